@@ -1,0 +1,617 @@
+// kernels.cuh -- the sm_100a kernels of the slice forward (exact mode).
+//
+// "Exact mode" = every rounding point and accumulation order of the reference's CPU path
+// (ggml's AVX2+FMA+F16C build) is reproduced, so hidden states are bit-identical:
+//   weight matmul   ggml_vec_dot_q4_0_q8_0 / q8_0_q8_0   ggml.c:2432-2455, 3313-3335, hsum 614-620
+//   act-quant       quantize_row_q8_0 (AVX branch)        ggml.c:1215-1252
+//   RMSNorm         ggml_compute_forward_rms_norm_f32     ggml.c:10309-10352 (+ ggml_mul 9062)
+//   RoPE            ggml_compute_forward_rope_f32 mode 0  ggml.c:11956-12055
+//   K.q / V.p       ggml_vec_dot_f16 + GGML_F32x8_REDUCE  ggml.c:2323-2357, 1895-1913
+//   softmax         ggml_compute_forward_soft_max_f32     ggml.c:11524-11590
+//   SiLU            ggml_vec_silu_f32 (GGML_SILU_FP16)    ggml.c:3541-3560
+// graph order: tensor_processor.cpp:537-766.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// =============================================================================================
+// Packed weight layout (HBM).  A matrix W[rows][K] of 32-wide blocks is cut into
+//   row-groups of 8 rows  x  quads of 4 consecutive blocks            -> one CHUNK
+//   tiles of TR row-groups (one CTA's rows), all quads of the tile contiguous, q-major:
+//       tile t : [q = 0..nbq) [rg = 0..TR) [chunk bytes]
+// Q4_0 chunk (576 B = the file's 18 B/block, nothing added):
+//       512 B : lane L = 4*r + w (r = row in group, w = 32-bit word of the 16 nibble bytes)
+//               holds 16 B = word w of blocks 4q..4q+3 of row r; nibbles stored as two's-complement
+//               4-bit (file nibble XOR 8), so `(x<<4)&0xF0F0F0F0` / `x&0xF0F0F0F0` are 16*(nibble-8)
+//               as signed bytes, ready for dp4a
+//        64 B : fp16 d of row r, blocks 4q..4q+3 at 512 + 8*r
+// Q8_0 chunk (1088 B = 34 B/block): 512 B words w of 4 blocks per lane, 512 B words w+4, 64 B scales.
+// A warp reads a chunk with one conflict-free LDS.128 (+ one LDS.64) per lane.
+// =============================================================================================
+constexpr int kWT_F16 = 1, kWT_Q4_0 = 2, kWT_Q8_0 = 8;
+constexpr int kQ4Chunk = 576, kQ8Chunk = 1088;
+constexpr int kWPC = 4;                 // consumer warps per CTA (8 rows x G groups each)
+constexpr int kConsumers = kWPC * 32;
+constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: int->float through the dp4a accumulator
+constexpr int kMagicI = 0x4B400000;
+
+__host__ __device__ constexpr int chunk_bytes(int wt) { return wt == kWT_Q4_0 ? kQ4Chunk : kQ8Chunk; }
+
+struct PackedW {
+    const uint8_t * data;
+    int wtype, rows, K, nb, nbq, TR, n_tiles;
+    long long tile_bytes;
+};
+
+// ---- repack: raw GGJT blocks -> packed layout (one thread per output 32-bit word) -----------
+// mode 0: single source; 1: three sources concatenated by rows (wq|wk|wv); 2: two sources with
+// row-groups interleaved (even = w1, odd = w3) so one warp owns row r of both for the SiLU gate.
+struct RepackArgs {
+    const uint8_t * src[3];
+    int mode, wtype, rows_per_src, nb, nbq, TR, n_tiles;
+    uint8_t * dst;
+};
+
+__global__ void k_repack(RepackArgs a) {
+    const int cb = chunk_bytes(a.wtype), words = cb / 4;
+    const long long total = (long long) a.n_tiles * a.nbq * a.TR * words;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int wi = (int)(i % words);
+        long long c = i / words;
+        const int rg = (int)(c % a.TR); c /= a.TR;
+        const int q = (int)(c % a.nbq);
+        const int tile = (int)(c / a.nbq);
+        const int gi = tile * a.TR + rg;                    // global row-group index
+        int s, sg;
+        if (a.mode == 1)      { const int gps = a.rows_per_src / 8; s = gi / gps; sg = gi % gps; }
+        else if (a.mode == 2) { s = gi & 1; sg = gi >> 1; }
+        else                  { s = 0; sg = gi; }
+        const int bsz = a.wtype == kWT_Q4_0 ? 18 : 34;
+        uint32_t out = 0;
+        const bool src_ok = s < 3 && a.src[s] != nullptr;
+        if (a.wtype == kWT_Q4_0) {
+            if (wi < 128) {                                  // nibble words
+                const int lane = wi >> 2, bq = wi & 3, r = lane >> 2, w = lane & 3;
+                const int row = sg * 8 + r, b = q * 4 + bq;
+                if (src_ok && row < a.rows_per_src && b < a.nb) {
+                    const uint8_t * blk = a.src[s] + ((long long) row * a.nb + b) * bsz;
+                    const uint16_t * p = (const uint16_t *)(blk + 2 + 4 * w);
+                    out = ((uint32_t) p[0] | ((uint32_t) p[1] << 16)) ^ 0x88888888u;
+                }
+            } else {                                         // scales: 16 words = 8 rows x 4 halves
+                const int h0 = (wi - 128) * 2;
+                uint32_t v[2] = {0, 0};
+                for (int k = 0; k < 2; k++) {
+                    const int r = (h0 + k) >> 2, bq = (h0 + k) & 3, row = sg * 8 + r, b = q * 4 + bq;
+                    if (src_ok && row < a.rows_per_src && b < a.nb)
+                        v[k] = *(const uint16_t *)(a.src[s] + ((long long) row * a.nb + b) * bsz);
+                }
+                out = v[0] | (v[1] << 16);
+            }
+        } else {                                             // Q8_0
+            if (wi < 256) {
+                const int half = wi >> 7, lw = wi & 127, lane = lw >> 2, bq = lw & 3, r = lane >> 2, w = (lane & 3) + 4 * half;
+                const int row = sg * 8 + r, b = q * 4 + bq;
+                if (src_ok && row < a.rows_per_src && b < a.nb) {
+                    const uint8_t * blk = a.src[s] + ((long long) row * a.nb + b) * bsz;
+                    const uint16_t * p = (const uint16_t *)(blk + 2 + 4 * w);
+                    out = (uint32_t) p[0] | ((uint32_t) p[1] << 16);
+                }
+            } else {
+                const int h0 = (wi - 256) * 2;
+                uint32_t v[2] = {0, 0};
+                for (int k = 0; k < 2; k++) {
+                    const int r = (h0 + k) >> 2, bq = (h0 + k) & 3, row = sg * 8 + r, b = q * 4 + bq;
+                    if (src_ok && row < a.rows_per_src && b < a.nb)
+                        v[k] = *(const uint16_t *)(a.src[s] + ((long long) row * a.nb + b) * bsz);
+                }
+                out = v[0] | (v[1] << 16);
+            }
+        }
+        ((uint32_t *) a.dst)[i] = out;
+    }
+}
+
+// =============================================================================================
+// K1: block-quantised weight matmul, exact mode (decode GEMV and NC-column prefill).
+//
+//   y[n][row] = hsum_l( fma_b( D_b, (float) sum_j w_j a_j, acc_l ) )      (ggml.c:2431-2455)
+//
+// Thread (r, w) of a consumer warp owns AVX lanes l = w and l = w+4 of row r: for every block it
+// takes ONE 32-bit word of nibbles, splits it into the two lanes' signed bytes, and runs two
+// dp4a -> fadd -> fma chains strictly in block order.  Parallelism comes from rows, never from K.
+//   * warp  = 8 rows x G row-groups; CTA = 4 consumer warps (+1 producer warp)
+//   * producer lane streams the tile's chunks with 1-D bulk async copies (UBLKCP) into a ring of
+//     NS stages guarded by full/empty mbarriers; it starts BEFORE griddepcontrol.wait because the
+//     weights never depend on the previous kernel -- the HBM stream runs across kernel boundaries
+//   * prologue (fused, per CTA): [RMSNorm * weight ->] Q8_0 act-quant of the input column(s) into
+//     shared memory in dp4a word order
+//   * epilogue (fused): store | + residual | SiLU(w1 x) * (w3 x)
+// =============================================================================================
+enum { PRO_PLAIN = 0, PRO_NORM = 1 };
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GATE = 2 };
+
+struct GemvArgs {
+    PackedW W;
+    const float * x;      int ldx;       // input  [N][ldx], K valid per row
+    const float * norm_w;                // PRO_NORM: weight [K]
+    const float * resid;  int ldr;       // EPI_RESID
+    float * y;            int ldy;       // output [N][ldy]
+    int N;                               // columns (tokens)
+    int out_rows;                        // valid output rows (E, 3E, or FF for the gate)
+    const uint16_t * tsilu;              // EPI_GATE: fp16 SiLU table (65536 entries)
+    int QS;                              // quads per ring stage
+    int NS;                              // ring stages
+};
+
+__host__ __device__ inline size_t act_bytes_per_col(int nbq) { return (size_t) nbq * (128 + 16); }
+
+template <int WT, int G, int NC, int PRO, int EPI, bool RING>
+__global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
+    constexpr int CB = (WT == kWT_Q4_0) ? kQ4Chunk : kQ8Chunk;
+    constexpr int TR = kWPC * G;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int nbq = a.W.nbq, K = a.W.K, nb = a.W.nb;
+    const int QS = a.QS, NS = a.NS;
+    const int stage_bytes = QS * TR * CB;
+    // smem carve-up: [ring NS*stage_bytes][act words NC*nbq*128][act scales NC*nbq*16][barriers][scratch]
+    uint8_t * ring = smem;
+    int * a_s = (int *)(smem + (RING ? (size_t) NS * stage_bytes : 0));
+    float * da_s = (float *)((uint8_t *) a_s + (size_t) NC * nbq * 128);
+    uint64_t * full = (uint64_t *)((uint8_t *) da_s + (size_t) NC * nbq * 16);
+    uint64_t * empty = full + 16;
+    double * red = (double *)(empty + 16);           // [kWPC] reduction scratch
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col0 = blockIdx.y * NC;
+    const int n_stage = (nbq + QS - 1) / QS;
+
+    if (RING) {
+        if (tid == 0) {
+            for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWPC); }
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+
+    if (RING && warp == kWPC) {
+        // ------------------------------------------------------------------ producer warp
+        if (lane == 0) {
+            grid_dep_launch();
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
+                const uint8_t * src = a.W.data + (long long) tile * a.W.tile_bytes;
+                for (int s = 0; s < n_stage; s++, it++) {
+                    const int slot = it % NS, use = it / NS;
+                    if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+                    const int q0 = s * QS, qn = min(QS, nbq - q0);
+                    const uint32_t bytes = (uint32_t) qn * TR * CB;
+                    mbar_arrive_expect_tx(&full[slot], bytes);
+                    bulk_g2s(ring + (size_t) slot * stage_bytes, src + (size_t) q0 * TR * CB, bytes, &full[slot]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    if (!RING && tid == 0) grid_dep_launch();
+    grid_dep_wait();                                   // input x comes from the previous kernel
+
+    // prologue: (norm +) quantise NC input columns into shared memory
+    for (int n = 0; n < NC; n++) {
+        const int col = col0 + n;
+        int * an = a_s + (size_t) n * nbq * 32;
+        float * dn = da_s + (size_t) n * nbq * 4;
+        if (col >= a.N) {                              // padded column: zeros
+            for (int i = tid; i < nbq * 32; i += kConsumers) an[i] = 0;
+            for (int i = tid; i < nbq * 4; i += kConsumers) dn[i] = 0.f;
+            continue;
+        }
+        const float * x = a.x + (size_t) col * a.ldx;
+        float scale = 1.0f;
+        if (PRO == PRO_NORM) {
+            double s = 0.0;
+            for (int i = tid * 4; i < K; i += kConsumers * 4) {
+                const float4 v = *(const float4 *)(x + i);
+                s += (double) fmul(v.x, v.x); s += (double) fmul(v.y, v.y);
+                s += (double) fmul(v.z, v.z); s += (double) fmul(v.w, v.w);
+            }
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) red[warp] = s;
+            named_bar_sync(1, kConsumers);
+            const double tot = (red[0] + red[1]) + (red[2] + red[3]);
+            named_bar_sync(1, kConsumers);
+            const float mean = (float)(tot / (double) K);
+            scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd(mean, 1e-6f)));
+        }
+        for (int b = tid; b < nbq * 4; b += kConsumers) {
+            const int Q = b >> 2, bq = b & 3;
+            int * dst = an + Q * 32 + bq * 2;          // [Q][w][bq][2]: + w*8 per word pair
+            if (b >= nb) {
+                for (int w = 0; w < 4; w++) { dst[w * 8] = 0; dst[w * 8 + 1] = 0; }
+                dn[b] = 0.f;
+                continue;
+            }
+            float v[32];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float4 t = *(const float4 *)(x + b * 32 + j * 4);
+                if (PRO == PRO_NORM) {
+                    const float4 wv = *(const float4 *)(a.norm_w + b * 32 + j * 4);
+                    t.x = fmul(fmul(t.x, scale), wv.x); t.y = fmul(fmul(t.y, scale), wv.y);
+                    t.z = fmul(fmul(t.z, scale), wv.z); t.w = fmul(fmul(t.w, scale), wv.w);
+                }
+                v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
+            }
+            float amax = 0.f;
+            #pragma unroll
+            for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
+            const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
+            const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
+            // Q4_0 path folds the 1/16 of the nibble placement into the activation scale (exact)
+            dn[b] = (WT == kWT_Q4_0) ? fmul(d, 0.0625f) : d;
+            #pragma unroll
+            for (int w = 0; w < 8; w++) {
+                uint32_t pk = 0;
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int qv = __float2int_rn(fmul(v[w*4 + j], id));
+                    pk |= ((uint32_t)(qv & 0xFF)) << (8 * j);
+                }
+                dst[(w & 3) * 8 + (w >> 2)] = (int) pk;
+            }
+        }
+    }
+    named_bar_sync(1, kConsumers);
+
+    const int r = lane >> 2, w = lane & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
+        float acc[G][NC][2];
+        #pragma unroll
+        for (int g = 0; g < G; g++)
+            #pragma unroll
+            for (int n = 0; n < NC; n++) { acc[g][n][0] = 0.f; acc[g][n][1] = 0.f; }
+        const uint8_t * gsrc = a.W.data + (long long) tile * a.W.tile_bytes;
+
+        for (int s = 0; s < n_stage; s++, it++) {
+            const int q0 = s * QS, qn = min(QS, nbq - q0);
+            const uint8_t * base;
+            int slot = 0;
+            if (RING) {
+                slot = it % NS;
+                mbar_wait(&full[slot], (it / NS) & 1);
+                base = ring + (size_t) slot * stage_bytes;
+            } else {
+                base = gsrc + (size_t) q0 * TR * CB;
+            }
+            for (int qi = 0; qi < qn; qi++) {
+                const int Q = q0 + qi;
+                uint4 wv[G], wv2[G]; uint2 sc[G];
+                #pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint8_t * ch = base + (size_t)(qi * TR + warp * G + g) * CB;
+                    wv[g] = *(const uint4 *)(ch + lane * 16);
+                    if (WT == kWT_Q8_0) { wv2[g] = *(const uint4 *)(ch + 512 + lane * 16); sc[g] = *(const uint2 *)(ch + 1024 + r * 8); }
+                    else sc[g] = *(const uint2 *)(ch + 512 + r * 8);
+                }
+                #pragma unroll
+                for (int n = 0; n < NC; n++) {
+                    const int4 * ap = (const int4 *)(a_s + (size_t) n * nbq * 32 + Q * 32 + w * 8);
+                    const int4 a01 = ap[0], a23 = ap[1];           // {lo0,hi0,lo1,hi1}, {lo2,hi2,lo3,hi3}
+                    const float4 dav = *(const float4 *)(da_s + (size_t) n * nbq * 4 + Q * 4);
+                    const int alo[4] = {a01.x, a01.z, a23.x, a23.z};
+                    const int ahi[4] = {a01.y, a01.w, a23.y, a23.w};
+                    const float da[4] = {dav.x, dav.y, dav.z, dav.w};
+                    #pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const uint32_t ww[4] = {wv[g].x, wv[g].y, wv[g].z, wv[g].w};
+                        const uint32_t ww2[4] = {wv2[g].x, wv2[g].y, wv2[g].z, wv2[g].w};
+                        const uint32_t sw[2] = {sc[g].x, sc[g].y};
+                        #pragma unroll
+                        for (int bq = 0; bq < 4; bq++) {
+                            const uint16_t dh = (uint16_t)(sw[bq >> 1] >> (16 * (bq & 1)));
+                            const float D = fmul(h2f(dh), da[bq]);
+                            int lo, hi;
+                            if (WT == kWT_Q4_0) { lo = (int)((ww[bq] << 4) & 0xF0F0F0F0u); hi = (int)(ww[bq] & 0xF0F0F0F0u); }
+                            else                { lo = (int) ww[bq]; hi = (int) ww2[bq]; }
+                            const float f0 = fadd(__int_as_float(__dp4a(lo, alo[bq], kMagicI)), -kMagic);
+                            const float f1 = fadd(__int_as_float(__dp4a(hi, ahi[bq], kMagicI)), -kMagic);
+                            acc[g][n][0] = ffma(D, f0, acc[g][n][0]);
+                            acc[g][n][1] = ffma(D, f1, acc[g][n][1]);
+                        }
+                    }
+                }
+            }
+            if (RING) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[slot]); }
+        }
+
+        // epilogue: hsum_float_8 order ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7))
+        float res[G][NC];
+        #pragma unroll
+        for (int g = 0; g < G; g++)
+            #pragma unroll
+            for (int n = 0; n < NC; n++) {
+                float t = fadd(acc[g][n][0], acc[g][n][1]);
+                t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 2));
+                t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 1));
+                res[g][n] = t;
+            }
+        if (w == 0) {
+            if (EPI == EPI_GATE) {
+                const int row = (tile * kWPC + warp) * 8 + r;
+                if (row < a.out_rows) {
+                    #pragma unroll
+                    for (int n = 0; n < NC; n++) {
+                        const int col = col0 + n;
+                        if (col < a.N) {
+                            const float sl = h2f(a.tsilu[f2h(res[0][n])]);
+                            a.y[(size_t) col * a.ldy + row] = fmul(sl, res[G - 1][n]);
+                        }
+                    }
+                }
+            } else {
+                #pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const int row = ((tile * kWPC + warp) * G + g) * 8 + r;
+                    if (row < a.out_rows) {
+                        #pragma unroll
+                        for (int n = 0; n < NC; n++) {
+                            const int col = col0 + n;
+                            if (col < a.N) {
+                                float v = res[g][n];
+                                if (EPI == EPI_RESID) v = fadd(v, a.resid[(size_t) col * a.ldr + row]);
+                                a.y[(size_t) col * a.ldy + row] = v;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// K1f: F16-weight matmul, exact mode: ggml_vec_dot_f16 (32 f32 slots, chunks of 32 in order,
+// fixed reduce tree, n%32 tail in double).  One warp per output row, lane = slot; weights are
+// re-laid at load as [row][c8 = chunk/8][lane][8 chunks] so each lane issues one 16 B load per
+// 8 chunks.  The activation row is rounded to fp16 (ggml_fp32_to_fp16_row, ggml.c:495-512).
+// =============================================================================================
+struct GemvF16Args {
+    const uint16_t * W;   // packed [rows][nc8][32][8]  (+ tail [rows][K%32] after, see tail)
+    const uint16_t * tail;
+    int rows, K;
+    const float * x; int ldx; const float * norm_w;
+    const float * resid; int ldr;
+    float * y; int ldy; int N;
+    const uint16_t * tsilu;
+    const uint16_t * W2; const uint16_t * tail2;   // EPI_GATE: second matrix (w3)
+};
+
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(256) k_gemv_f16(const GemvF16Args a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t * xh = (uint16_t *) smem;               // [K] fp16 activation
+    __shared__ double red[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, K = a.K;
+    const int col = blockIdx.y;
+    grid_dep_wait();
+    const float * x = a.x + (size_t) col * a.ldx;
+    float scale = 1.0f;
+    if (PRO == PRO_NORM) {
+        double s = 0.0;
+        for (int i = tid; i < K; i += 256) s += (double) fmul(x[i], x[i]);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        double tot = 0.0;
+        for (int i = 0; i < 8; i++) tot += red[i];
+        scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) K), 1e-6f)));
+    }
+    for (int i = tid; i < K; i += 256) {
+        float v = x[i];
+        if (PRO == PRO_NORM) v = fmul(fmul(v, scale), a.norm_w[i]);
+        xh[i] = f2h(v);
+    }
+    __syncthreads();
+    const int nchunk = K / 32, nc8 = (nchunk + 7) / 8, ntail = K & 31;
+    for (int row = blockIdx.x * 8 + warp; row < a.rows; row += gridDim.x * 8) {
+        float res[2] = {0.f, 0.f};
+        #pragma unroll
+        for (int m = 0; m < (EPI == EPI_GATE ? 2 : 1); m++) {
+            const uint16_t * Wm = m ? a.W2 : a.W;
+            const uint16_t * tl = m ? a.tail2 : a.tail;
+            float acc = 0.f;
+            const uint4 * wp = (const uint4 *)(Wm + ((size_t) row * nc8 * 32 + lane) * 8);
+            for (int c8 = 0; c8 < nc8; c8++) {
+                const uint4 v = wp[(size_t) c8 * 32];
+                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+                #pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int c = c8 * 8 + j;
+                    if (c < nchunk) {
+                        const uint16_t wh = (uint16_t)(u[j >> 1] >> (16 * (j & 1)));
+                        acc = ffma(h2f(wh), h2f(xh[c * 32 + lane]), acc);
+                    }
+                }
+            }
+            // slots s = 8*j + l: (x0+x2)+(x1+x3) -> xor 16, xor 8; lo128+hi128 -> xor 4; hadd, hadd -> xor 1, xor 2
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 16));
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 8));
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+            double sumf = (double) acc;
+            for (int i = 0; i < ntail; i++)
+                sumf += (double) fmul(h2f(tl[(size_t) row * ntail + i]), h2f(xh[nchunk * 32 + i]));
+            res[m] = (float) sumf;
+        }
+        if (lane == 0) {
+            float v = res[0];
+            if (EPI == EPI_RESID) v = fadd(v, a.resid[(size_t) col * a.ldr + row]);
+            if (EPI == EPI_GATE)  v = fmul(h2f(a.tsilu[f2h(res[0])]), res[1]);
+            a.y[(size_t) col * a.ldy + row] = v;
+        }
+    }
+}
+
+// repack F16 weights [rows][K] -> [rows][nc8][32 lanes][8 chunks] (+ tail [rows][K%32])
+__global__ void k_repack_f16(const uint16_t * src, uint16_t * dst, uint16_t * tail, int rows, int K) {
+    const int nchunk = K / 32, nc8 = (nchunk + 7) / 8, ntail = K & 31;
+    const long long total = (long long) rows * nc8 * 256;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int j = (int)(i & 7), lane = (int)((i >> 3) & 31);
+        const long long rc = i >> 8; const int c8 = (int)(rc % nc8); const long long row = rc / nc8;
+        const int c = c8 * 8 + j;
+        dst[i] = c < nchunk ? src[row * K + c * 32 + lane] : (uint16_t) 0;
+    }
+    const long long tt = (long long) rows * ntail;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < tt; i += (long long) gridDim.x * blockDim.x)
+        tail[i] = src[(i / ntail) * K + nchunk * 32 + (i % ntail)];
+}
+
+// =============================================================================================
+// K4: RoPE (q, k) + KV append.  qkv [N][3E] f32 -> q16 [N][E] (fp16, the rounding mul_mat applies
+// to src1), K cache [pos][E] fp16 (post-RoPE), V cache [pos][E] fp16.  cos/sin come from a host
+// table built with the host libm, theta iterated in f32 exactly as ggml.c:12000-12044.
+// =============================================================================================
+struct RopeArgs {
+    const float * qkv; int E, H, D, N;
+    const int * n_past;
+    const float2 * cs;            // [n_ctx][D/2] (cos, sin)
+    uint16_t * q16; uint16_t * kc; uint16_t * vc;   // kc/vc: this layer's cache base
+};
+
+__global__ void k_rope_append(const RopeArgs a) {
+    grid_dep_launch();
+    grid_dep_wait();
+    const int n = blockIdx.y, pos = *a.n_past + n, half = a.D / 2;
+    const float * row = a.qkv + (size_t) n * 3 * a.E;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.E / 2; p += gridDim.x * blockDim.x) {
+        const int j = p % half;
+        const float2 cs = a.cs[(size_t) pos * half + j];
+        const float2 q = *(const float2 *)(row + 2 * p);
+        const float2 k = *(const float2 *)(row + a.E + 2 * p);
+        const float2 v = *(const float2 *)(row + 2 * a.E + 2 * p);
+        const float q0 = fsub(fmul(q.x, cs.x), fmul(q.y, cs.y)), q1 = fadd(fmul(q.x, cs.y), fmul(q.y, cs.x));
+        const float k0 = fsub(fmul(k.x, cs.x), fmul(k.y, cs.y)), k1 = fadd(fmul(k.x, cs.y), fmul(k.y, cs.x));
+        *(uint32_t *)(a.q16 + (size_t) n * a.E + 2 * p) = (uint32_t) f2h(q0) | ((uint32_t) f2h(q1) << 16);
+        *(uint32_t *)(a.kc + (size_t) pos * a.E + 2 * p) = (uint32_t) f2h(k0) | ((uint32_t) f2h(k1) << 16);
+        *(uint32_t *)(a.vc + (size_t) pos * a.E + 2 * p) = (uint32_t) f2h(v.x) | ((uint32_t) f2h(v.y) << 16);
+    }
+}
+
+// =============================================================================================
+// K5: attention for one (head, query token), exact mode.
+//   scores  s_t = f32( dot_f16(K[t], q16) * 1/sqrt(d) ),  t <= n_past + n      (mask, ggml.c:11476)
+//   softmax e_t = EXP_TABLE[fp16(s_t - max)], S in double, p_t = e_t * (float)(1/S), rounded to fp16
+//   out_c   = dot_f16(V[0..T)[c], p16[0..T)),  T = n_past + N  (the split into 32-slot body and
+//             double tail follows the FULL row length T, masked entries contribute exact zeros)
+// One warp = one K.q dot (lane = slot); V.p: thread (g, c) owns slots 8g..8g+7 of channel c.
+// =============================================================================================
+struct AttnArgs {
+    const uint16_t * q16; const uint16_t * kc; const uint16_t * vc;
+    const int * n_past; int E, H, D, N;
+    const uint16_t * texp;
+    float * out;                  // [N][E]
+    float kq_scale;
+};
+
+__global__ void __launch_bounds__(512) k_attention(const AttnArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    grid_dep_launch();
+    grid_dep_wait();
+    const int h = blockIdx.x, n = blockIdx.y, D = a.D, E = a.E;
+    const int n_past = *a.n_past, T = n_past + a.N, tcount = n_past + n + 1;
+    float * sc = (float *) smem;                                   // [T]
+    uint16_t * p16 = (uint16_t *)(sc + ((T + 3) & ~3));            // [T]
+    float * part = (float *)(p16 + ((T + 7) & ~7));                // [4][D][8]
+    __shared__ double redd[16]; __shared__ float redf[16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+
+    // ---- scores
+    const int np = D & ~31, nch = np >> 5;
+    const uint16_t * q = a.q16 + (size_t) n * E + h * D;
+    float qf[8];
+    #pragma unroll
+    for (int c = 0; c < 8; c++) qf[c] = c < nch ? h2f(q[c * 32 + lane]) : 0.f;
+    for (int t = warp; t < tcount; t += nwarp) {
+        const uint16_t * k = a.kc + (size_t) t * E + h * D;
+        float acc = 0.f;
+        #pragma unroll
+        for (int c = 0; c < 8; c++) if (c < nch) acc = ffma(h2f(k[c * 32 + lane]), qf[c], acc);
+        acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 16));
+        acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 8));
+        acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+        acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+        acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+        if (lane == 0) {
+            double sumf = (double) acc;
+            for (int i = np; i < D; i++) sumf += (double) fmul(h2f(k[i]), h2f(q[i]));
+            sc[t] = fmul((float) sumf, a.kq_scale);
+        }
+    }
+    __syncthreads();
+
+    // ---- softmax over t < tcount
+    float mx = -INFINITY;
+    for (int t = tid; t < tcount; t += blockDim.x) mx = fmaxf(mx, sc[t]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) redf[warp] = mx;
+    __syncthreads();
+    mx = redf[0];
+    for (int i = 1; i < nwarp; i++) mx = fmaxf(mx, redf[i]);
+    double s = 0.0;
+    for (int t = tid; t < tcount; t += blockDim.x) {
+        const float e = h2f(a.texp[f2h(fsub(sc[t], mx))]);
+        sc[t] = e; s += (double) e;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) redd[warp] = s;
+    __syncthreads();
+    double S = 0.0;
+    for (int i = 0; i < nwarp; i++) S += redd[i];                 // fp16-valued terms: exact in any order
+    const float inv = (float)(1.0 / S);
+    for (int t = tid; t < tcount; t += blockDim.x) p16[t] = f2h(fmul(sc[t], inv));
+    __syncthreads();
+
+    // ---- V . p
+    const int npT = T & ~31;
+    const int g = tid / D, c = tid - g * D;
+    if (g < 4) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint16_t * v = a.vc + h * D + c;
+        const int lim = min(npT, tcount);
+        for (int base = 8 * g; base < lim; base += 32) {
+            #pragma unroll
+            for (int l = 0; l < 8; l++) {
+                const int t = base + l;
+                if (t < lim) acc[l] = ffma(h2f(v[(size_t) t * E]), h2f(p16[t]), acc[l]);
+            }
+        }
+        #pragma unroll
+        for (int l = 0; l < 8; l++) part[(g * D + c) * 8 + l] = acc[l];
+    }
+    __syncthreads();
+    if (tid < D) {
+        float vv[8];
+        #pragma unroll
+        for (int l = 0; l < 8; l++) {
+            const float a0 = fadd(part[(0 * D + tid) * 8 + l], part[(2 * D + tid) * 8 + l]);
+            const float a1 = fadd(part[(1 * D + tid) * 8 + l], part[(3 * D + tid) * 8 + l]);
+            vv[l] = fadd(a0, a1);
+        }
+        const float t0 = fadd(vv[0], vv[4]), t1 = fadd(vv[1], vv[5]), t2 = fadd(vv[2], vv[6]), t3 = fadd(vv[3], vv[7]);
+        double sumf = (double) fadd(fadd(t0, t1), fadd(t2, t3));
+        const uint16_t * v = a.vc + h * D + tid;
+        for (int t = npT; t < tcount; t++) sumf += (double) fmul(h2f(v[(size_t) t * E]), h2f(p16[t]));
+        a.out[(size_t) n * E + h * D + tid] = (float) sumf;
+    }
+}
+
+// position counter kept on the device so a captured graph can be replayed for every token
+__global__ void k_advance(int * n_past, int by) { grid_dep_wait(); if (threadIdx.x == 0) *n_past += by; }
+
+}  // namespace b200

@@ -1,0 +1,565 @@
+// runtime.cu -- slice handle, loader, forward scheduling and the C ABI (include/b200_slice.h).
+//
+// Replaces TransformerSlice / llama_eval_internal / the loader of the reference
+// (distllm/tensor_processor.cpp:1488-1562, 474-809, 926-1086, 1203-1416) for a slice resident on
+// one B200.  One stream per slice; the N=1 decode step is a CUDA graph replayed per token with
+// the position kept in device memory.
+#include "kernels.cuh"
+#include "ggjt_file.hpp"
+
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace b200 {
+
+constexpr int kSmemLimit = 226 * 1024;   // opt-in dynamic limit is 227 KB minus static __shared__
+
+struct LayerW {
+    PackedW qkv{}, wo{}, w13{}, w2{};
+    // F16-weight slices
+    uint16_t * f_q = nullptr, * f_k = nullptr, * f_v = nullptr, * f_o = nullptr, * f_1 = nullptr, * f_2 = nullptr, * f_3 = nullptr;
+    float * attn_norm = nullptr, * ffn_norm = nullptr;
+};
+
+struct GraphKey { const float * in; float * out; bool host; bool operator<(const GraphKey & o) const {
+    return in != o.in ? in < o.in : (out != o.out ? out < o.out : host < o.host); } };
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_slice {
+    int device = 0, n_sm = 148;
+    cudaStream_t stream = nullptr;
+    int E = 0, H = 0, D = 0, FF = 0, L = 0, first_layer = 0, n_ctx = 512, wtype = 0;
+    int n_past = 0;
+    int * d_npast = nullptr;
+    std::vector<LayerW> layers;
+    std::vector<void *> allocs;
+    uint16_t * kc = nullptr, * vc = nullptr, * q16 = nullptr;
+    float * xa = nullptr, * xb = nullptr, * qkv = nullptr, * att = nullptr, * ffin = nullptr, * gate = nullptr;
+    float * d_in = nullptr, * d_out = nullptr, * h_in = nullptr, * h_out = nullptr;
+    float2 * cs = nullptr; uint16_t * texp = nullptr, * tsilu = nullptr;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
+    int64_t launches = 0, weight_bytes = 0;
+    bool use_ring = true, use_graph = true, use_pdl = false;
+    int opt_ns = 0, opt_qs = 0, opt_cta_per_sm = 0;
+    std::mutex mu;
+    // pipeline (pipeline.cu)
+    void * pipe = nullptr;
+};
+
+namespace b200 {
+
+static int env_int(const char * name, int dflt) { const char * v = getenv(name); return v ? atoi(v) : dflt; }
+
+template <typename T> static int dev_alloc(b200_slice * s, T ** p, size_t n) {
+    void * q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail(B200_ECUDA, "cudaMalloc(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    s->allocs.push_back(q); *p = (T *) q; return 0;
+}
+
+// ---------------------------------------------------------------- kernel dispatch
+template <int WT, int G, int NC, int PRO, int EPI, bool RING>
+static int launch_gemv_t(b200_slice * s, GemvArgs a) {
+    constexpr int CB = (WT == kWT_Q4_0) ? kQ4Chunk : kQ8Chunk;
+    constexpr int TR = kWPC * G;
+    auto kern = k_gemv<WT, G, NC, PRO, EPI, RING>;
+    static bool attr_set[16] = {false};
+    int QS = s->opt_qs > 0 ? s->opt_qs : 8 / G;
+    if (QS > a.W.nbq) QS = a.W.nbq;
+    const size_t stage = (size_t) QS * TR * CB;
+    const size_t act = (size_t) NC * act_bytes_per_col(a.W.nbq) + 32 * 8 + kWPC * 8 + 64;
+    int NS = RING ? (s->opt_ns > 0 ? s->opt_ns : 4) : 0;
+    while (NS > 2 && NS * stage + act > (size_t) kSmemLimit) NS--;
+    if (NS > 16) NS = 16;
+    const size_t smem = NS * stage + act;
+    if (smem > (size_t) kSmemLimit) return fail(B200_EINVAL, "gemv needs %zu B of shared memory (K=%d, NC=%d)", smem, a.W.K, NC);
+    if (!attr_set[s->device & 15]) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr_set[s->device & 15] = true;
+    }
+    a.QS = QS; a.NS = NS;
+    int per_sm = s->opt_cta_per_sm > 0 ? s->opt_cta_per_sm : (int)(kSmemLimit / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    const int ncol = (a.N + NC - 1) / NC;
+    int gx = a.W.n_tiles;
+    const int cap = s->n_sm * per_sm;
+    if (gx > cap) gx = cap;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(gx, ncol, 1);
+    cfg.blockDim = dim3(RING ? kConsumers + 32 : kConsumers, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    s->launches++;
+    return 0;
+}
+
+template <int WT, int G, int PRO, int EPI>
+static int launch_gemv_nc(b200_slice * s, const GemvArgs & a) {
+    if (a.N == 1) return s->use_ring ? launch_gemv_t<WT, G, 1, PRO, EPI, true>(s, a) : launch_gemv_t<WT, G, 1, PRO, EPI, false>(s, a);
+    return s->use_ring ? launch_gemv_t<WT, G, 8, PRO, EPI, true>(s, a) : launch_gemv_t<WT, G, 8, PRO, EPI, false>(s, a);
+}
+
+template <int G, int PRO, int EPI>
+static int launch_gemv(b200_slice * s, const GemvArgs & a) {
+    if (a.W.wtype == kWT_Q4_0) return launch_gemv_nc<kWT_Q4_0, G, PRO, EPI>(s, a);
+    return launch_gemv_nc<kWT_Q8_0, G, PRO, EPI>(s, a);
+}
+
+template <typename K, typename A>
+static int launch_simple(b200_slice * s, K kern, dim3 grid, dim3 block, size_t smem, const A & args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    s->launches++;
+    return 0;
+}
+
+template <int PRO, int EPI>
+static int launch_f16(b200_slice * s, GemvF16Args a) {
+    auto kern = k_gemv_f16<PRO, EPI>;
+    static bool attr_set[16] = {false};
+    const size_t smem = (size_t) a.K * 2 + 16;
+    if (!attr_set[s->device & 15]) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        attr_set[s->device & 15] = true;
+    }
+    int gx = (a.rows + 7) / 8;
+    const int cap = s->n_sm * 8;
+    if (gx > cap) gx = cap;
+    return launch_simple(s, kern, dim3(gx, a.N, 1), dim3(256, 1, 1), smem, a);
+}
+
+// ---------------------------------------------------------------- one forward over the slice
+// Enqueue every layer for N tokens at device-side position *d_npast (tensor_processor.cpp:537-766).
+static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) {
+    const int E = s->E, FF = s->FF, H = s->H, D = s->D;
+    const float * cur = in;
+    for (int il = 0; il < s->L; il++) {
+        LayerW & Lw = s->layers[il];
+        float * nxt = (il == s->L - 1) ? out : ((il & 1) ? s->xb : s->xa);
+        uint16_t * kc = s->kc + (size_t) il * s->n_ctx * E, * vc = s->vc + (size_t) il * s->n_ctx * E;
+        int rc;
+        if (s->wtype == kWT_F16) {
+            GemvF16Args f{}; f.K = E; f.x = cur; f.ldx = E; f.norm_w = Lw.attn_norm; f.N = N; f.tsilu = s->tsilu;
+            f.rows = E; f.ldy = 3 * E;
+            f.W = Lw.f_q; f.y = s->qkv;         if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
+            f.W = Lw.f_k; f.y = s->qkv + E;     if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
+            f.W = Lw.f_v; f.y = s->qkv + 2 * E; if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
+        } else {
+            GemvArgs g{}; g.W = Lw.qkv; g.x = cur; g.ldx = E; g.norm_w = Lw.attn_norm; g.y = s->qkv; g.ldy = 3 * E;
+            g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu;
+            if ((rc = launch_gemv<1, PRO_NORM, EPI_STORE>(s, g))) return rc;
+        }
+        RopeArgs ra{s->qkv, E, H, D, N, s->d_npast, s->cs, s->q16, kc, vc};
+        if ((rc = launch_simple(s, k_rope_append, dim3((E / 2 + 255) / 256, N, 1), dim3(256, 1, 1), 0, ra))) return rc;
+        AttnArgs aa{s->q16, kc, vc, s->d_npast, E, H, D, N, s->texp, s->att, 1.0f / sqrtf((float) E / (float) H)};
+        const size_t asm_bytes = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + (size_t) 4 * D * 8 * 4 + 64;
+        if ((rc = launch_simple(s, k_attention, dim3(H, N, 1), dim3(512, 1, 1), asm_bytes, aa))) return rc;
+        if (s->wtype == kWT_F16) {
+            GemvF16Args f{}; f.K = E; f.x = s->att; f.ldx = E; f.N = N; f.tsilu = s->tsilu;
+            f.rows = E; f.W = Lw.f_o; f.resid = cur; f.ldr = E; f.y = s->ffin; f.ldy = E;
+            if ((rc = launch_f16<PRO_PLAIN, EPI_RESID>(s, f))) return rc;
+            GemvF16Args g{}; g.K = E; g.x = s->ffin; g.ldx = E; g.norm_w = Lw.ffn_norm; g.N = N; g.tsilu = s->tsilu;
+            g.rows = FF; g.W = Lw.f_1; g.W2 = Lw.f_3; g.y = s->gate; g.ldy = FF;
+            if ((rc = launch_f16<PRO_NORM, EPI_GATE>(s, g))) return rc;
+            GemvF16Args w{}; w.K = FF; w.x = s->gate; w.ldx = FF; w.N = N; w.tsilu = s->tsilu;
+            w.rows = E; w.W = Lw.f_2; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
+            if ((rc = launch_f16<PRO_PLAIN, EPI_RESID>(s, w))) return rc;
+        } else {
+            GemvArgs o{}; o.W = Lw.wo; o.x = s->att; o.ldx = E; o.resid = cur; o.ldr = E; o.y = s->ffin; o.ldy = E;
+            o.N = N; o.out_rows = E; o.tsilu = s->tsilu;
+            if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID>(s, o))) return rc;
+            GemvArgs g{}; g.W = Lw.w13; g.x = s->ffin; g.ldx = E; g.norm_w = Lw.ffn_norm; g.y = s->gate; g.ldy = FF;
+            g.N = N; g.out_rows = FF; g.tsilu = s->tsilu;
+            if ((rc = launch_gemv<2, PRO_NORM, EPI_GATE>(s, g))) return rc;
+            GemvArgs w{}; w.W = Lw.w2; w.x = s->gate; w.ldx = FF; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
+            w.N = N; w.out_rows = E; w.tsilu = s->tsilu;
+            if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID>(s, w))) return rc;
+        }
+        cur = nxt;
+    }
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+        B200_CUDA(cudaLaunchKernelEx(&cfg, k_advance, s->d_npast, N));
+        s->launches++;
+    }
+    return 0;
+}
+
+// N = 1: replay a captured graph (host variant adds the H2D / D2H copies as graph nodes)
+static int run_decode_graph(b200_slice * s, const float * in, float * out, bool host) {
+    GraphKey key{in, out, host};
+    auto it = s->graphs.find(key);
+    const int per_step = 6 * s->L + (s->wtype == kWT_F16 ? 2 * s->L : 0) + 1;
+    if (it == s->graphs.end()) {
+        const int64_t before = s->launches;
+        cudaGraph_t g = nullptr;
+        B200_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        if (host) {
+            cudaMemcpyAsync(s->d_in, s->h_in, (size_t) s->E * 4, cudaMemcpyHostToDevice, s->stream);
+            rc = enqueue_layers(s, s->d_in, 1, s->d_out);
+            cudaMemcpyAsync(s->h_out, s->d_out, (size_t) s->E * 4, cudaMemcpyDeviceToHost, s->stream);
+        } else {
+            rc = enqueue_layers(s, in, 1, out);
+        }
+        cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+        s->launches = before;
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(B200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        cudaGraphExec_t ge = nullptr;
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(B200_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        if (s->graphs.size() >= 8) { for (auto & kv : s->graphs) cudaGraphExecDestroy(kv.second); s->graphs.clear(); }
+        it = s->graphs.emplace(key, ge).first;
+    }
+    B200_CUDA(cudaGraphLaunch(it->second, s->stream));
+    s->launches += per_step;
+    return 0;
+}
+
+static int forward_locked(b200_slice * s, const float * in, int N, float * out, bool host) {
+    if (N <= 0) return fail(B200_EINVAL, "n_tokens must be positive (got %d)", N);
+    if (s->n_past + N > s->n_ctx)
+        return fail(B200_ECONTEXT, "context overflow: n_past %d + n_tokens %d > n_ctx %d", s->n_past, N, s->n_ctx);
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaEventRecord(s->ev0, s->stream));
+    int rc;
+    if (host) {
+        if (N == 1 && s->use_graph) {
+            memcpy(s->h_in, in, (size_t) s->E * 4);
+            if ((rc = run_decode_graph(s, nullptr, nullptr, true))) return rc;
+            B200_CUDA(cudaEventRecord(s->ev1, s->stream));
+            B200_CUDA(cudaStreamSynchronize(s->stream));
+            memcpy(out, s->h_out, (size_t) s->E * 4);
+        } else {
+            B200_CUDA(cudaMemcpyAsync(s->d_in, in, (size_t) N * s->E * 4, cudaMemcpyHostToDevice, s->stream));
+            if ((rc = enqueue_layers(s, s->d_in, N, s->d_out))) return rc;
+            B200_CUDA(cudaEventRecord(s->ev1, s->stream));
+            B200_CUDA(cudaMemcpyAsync(out, s->d_out, (size_t) N * s->E * 4, cudaMemcpyDeviceToHost, s->stream));
+            B200_CUDA(cudaStreamSynchronize(s->stream));
+        }
+    } else {
+        if (N == 1 && s->use_graph) { if ((rc = run_decode_graph(s, in, out, false))) return rc; }
+        else if ((rc = enqueue_layers(s, in, N, out))) return rc;
+        B200_CUDA(cudaEventRecord(s->ev1, s->stream));
+    }
+    s->timed = true;
+    s->n_past += N;
+    return 0;
+}
+
+// ---------------------------------------------------------------- loader
+// Pageable H2D copies return before the DMA lands; keep them on the slice's stream so the
+// repack kernel that follows is ordered after them.
+static int upload_raw(b200_slice * s, const GgjtFile & f, const GgjtTensor & t, uint8_t * dst) {
+    B200_CUDA(cudaMemcpyAsync(dst, f.data(t), t.nbytes, cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+static int pack_matrix(b200_slice * s, const GgjtFile & f, const GgjtTensor * const * src, int nsrc, int mode, int G,
+                       uint8_t * scratch, PackedW * out) {
+    const int wt = (int) src[0]->type;
+    const int K = (int) src[0]->ne[0], rows_per = (int) src[0]->ne[1];
+    const int nb = K / 32, nbq = (nb + 3) / 4, TR = kWPC * G;
+    const int total_groups = (rows_per + 7) / 8 * nsrc;
+    const int n_tiles = (total_groups + TR - 1) / TR;
+    const int cb = chunk_bytes(wt);
+    const long long tile_bytes = (long long) nbq * TR * cb;
+    uint8_t * dst = nullptr;
+    int rc = dev_alloc(s, &dst, (size_t) n_tiles * tile_bytes);
+    if (rc) return rc;
+    RepackArgs ra{};
+    size_t off = 0;
+    for (int i = 0; i < nsrc; i++) {
+        if ((rc = upload_raw(s, f, *src[i], scratch + off))) return rc;
+        ra.src[i] = scratch + off;
+        off += (src[i]->nbytes + 255) & ~(size_t) 255;
+    }
+    ra.mode = mode; ra.wtype = wt; ra.rows_per_src = rows_per; ra.nb = nb; ra.nbq = nbq; ra.TR = TR; ra.n_tiles = n_tiles;
+    ra.dst = dst;
+    k_repack<<<s->n_sm * 8, 256, 0, s->stream>>>(ra);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    out->data = dst; out->wtype = wt; out->rows = rows_per * nsrc; out->K = K; out->nb = nb; out->nbq = nbq; out->TR = TR;
+    out->n_tiles = n_tiles; out->tile_bytes = tile_bytes;
+    return 0;
+}
+
+static int pack_f16(b200_slice * s, const GgjtFile & f, const GgjtTensor & t, uint8_t * scratch, uint16_t ** out) {
+    const int K = (int) t.ne[0], rows = (int) t.ne[1];
+    const int nchunk = K / 32, nc8 = (nchunk + 7) / 8;
+    uint16_t * dst = nullptr;
+    int rc = dev_alloc(s, &dst, (size_t) rows * nc8 * 256 + 8);
+    if (rc) return rc;
+    if ((rc = upload_raw(s, f, t, scratch))) return rc;
+    k_repack_f16<<<s->n_sm * 8, 256, 0, s->stream>>>((const uint16_t *) scratch, dst, dst /*no tail: K%32==0*/, rows, K);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    *out = dst;
+    return 0;
+}
+
+static int build_tables(b200_slice * s) {
+    // fp16 lookup tables of ggml_init (ggml.c:4300-4312), built with the host libm like the reference does
+    std::vector<uint16_t> texp(65536), tsilu(65536);
+    for (int i = 0; i < 65536; i++) {
+        const float f = __half2float(__ushort_as_half((unsigned short) i));
+        texp[i]  = __half_as_ushort(__float2half_rn(expf(f)));
+        tsilu[i] = __half_as_ushort(__float2half_rn(f / (1.0f + expf(-f))));
+    }
+    int rc;
+    if ((rc = dev_alloc(s, &s->texp, 65536)) || (rc = dev_alloc(s, &s->tsilu, 65536))) return rc;
+    B200_CUDA(cudaMemcpy(s->texp, texp.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(s->tsilu, tsilu.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    // RoPE cos/sin, theta iterated in f32 (ggml.c:12000, 12038-12044)
+    const int half = s->D / 2;
+    std::vector<float2> cs((size_t) s->n_ctx * half);
+    const float theta_scale = powf(10000.0, -2.0f / s->D);
+    for (int p = 0; p < s->n_ctx; p++) {
+        float theta = (float) p;
+        for (int j = 0; j < half; j++) {
+            cs[(size_t) p * half + j] = make_float2(cosf(theta), sinf(theta));
+            theta *= theta_scale;
+        }
+    }
+    if ((rc = dev_alloc(s, &s->cs, cs.size()))) return rc;
+    B200_CUDA(cudaMemcpy(s->cs, cs.data(), cs.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int load_locked(b200_slice * s, const char * path) {
+    std::unique_ptr<GgjtFile> fp;
+    try { fp.reset(new GgjtFile(path, false)); }
+    catch (const std::exception & e) { return fail(B200_EFILE, "error loading model: %s", e.what()); }
+    GgjtFile & f = *fp;
+    if (f.n_layer == 0 || f.n_head == 0 || f.n_embd % f.n_head || f.n_embd % 32)
+        return fail(B200_EFILE, "not a transformer slice file (n_layer=%u n_embd=%u n_head=%u)", f.n_layer, f.n_embd, f.n_head);
+    s->E = (int) f.n_embd; s->H = (int) f.n_head; s->D = s->E / s->H; s->L = (int) f.n_layer; s->first_layer = (int) f.first_layer;
+    s->FF = (int)(((2 * (4 * f.n_embd) / 3 + f.n_mult - 1) / f.n_mult) * f.n_mult);   // tensor_processor.cpp:1250
+    if (s->D > 128 || (s->D & 1)) return fail(B200_EFILE, "head size %d unsupported (<=128, even)", s->D);
+    const uint32_t E = f.n_embd, FF = (uint32_t) s->FF;
+    s->layers.resize(s->L);
+    uint8_t * scratch = nullptr;
+    int rc;
+    try {
+        const std::string p0 = "layers." + std::to_string(s->first_layer);
+        s->wtype = (int) f.get(p0 + ".attention.wq.weight", {E, E}).type;
+        if (s->wtype != kWT_Q4_0 && s->wtype != kWT_Q8_0 && s->wtype != kWT_F16)
+            return fail(B200_EFILE, "weight type %d unsupported (Q4_0, Q8_0, F16)", s->wtype);
+        const size_t big = GgjtFile::type_bytes(s->wtype, (size_t) E * FF) + 4096;
+        B200_CUDA(cudaMalloc((void **) &scratch, 3 * big));
+        for (int i = 0; i < s->L; i++) {
+            const std::string p = "layers." + std::to_string(i + s->first_layer);
+            LayerW & Lw = s->layers[i];
+            const GgjtTensor & an = f.get(p + ".attention_norm.weight", {E});
+            const GgjtTensor & wq = f.get(p + ".attention.wq.weight", {E, E});
+            const GgjtTensor & wk = f.get(p + ".attention.wk.weight", {E, E});
+            const GgjtTensor & wv = f.get(p + ".attention.wv.weight", {E, E});
+            const GgjtTensor & wo = f.get(p + ".attention.wo.weight", {E, E});
+            const GgjtTensor & fn = f.get(p + ".ffn_norm.weight", {E});
+            const GgjtTensor & w1 = f.get(p + ".feed_forward.w1.weight", {E, FF});
+            const GgjtTensor & w2 = f.get(p + ".feed_forward.w2.weight", {FF, E});
+            const GgjtTensor & w3 = f.get(p + ".feed_forward.w3.weight", {E, FF});
+            if (an.type != GT_F32 || fn.type != GT_F32) { cudaFree(scratch); return fail(B200_EFILE, "norm weights must be F32"); }
+            for (const GgjtTensor * t : {&wq, &wk, &wv, &wo, &w1, &w2, &w3})
+                if ((int) t->type != s->wtype) { cudaFree(scratch); return fail(B200_EFILE, "mixed weight types in slice (%s)", t->name.c_str()); }
+            if ((rc = dev_alloc(s, &Lw.attn_norm, E)) || (rc = dev_alloc(s, &Lw.ffn_norm, E))) { cudaFree(scratch); return rc; }
+            cudaMemcpy(Lw.attn_norm, f.data(an), E * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(Lw.ffn_norm, f.data(fn), E * 4, cudaMemcpyHostToDevice);
+            if (s->wtype == kWT_F16) {
+                const GgjtTensor * ts[7] = {&wq, &wk, &wv, &wo, &w1, &w2, &w3};
+                uint16_t ** dst[7] = {&Lw.f_q, &Lw.f_k, &Lw.f_v, &Lw.f_o, &Lw.f_1, &Lw.f_2, &Lw.f_3};
+                for (int k = 0; k < 7; k++) if ((rc = pack_f16(s, f, *ts[k], scratch, dst[k]))) { cudaFree(scratch); return rc; }
+            } else {
+                const GgjtTensor * qkv[3] = {&wq, &wk, &wv};
+                const GgjtTensor * o1[1] = {&wo};
+                const GgjtTensor * g13[2] = {&w1, &w3};
+                const GgjtTensor * d2[1] = {&w2};
+                if ((rc = pack_matrix(s, f, qkv, 3, 1, 1, scratch, &Lw.qkv)) ||
+                    (rc = pack_matrix(s, f, o1, 1, 0, 1, scratch, &Lw.wo)) ||
+                    (rc = pack_matrix(s, f, g13, 2, 2, 2, scratch, &Lw.w13)) ||
+                    (rc = pack_matrix(s, f, d2, 1, 0, 1, scratch, &Lw.w2))) { cudaFree(scratch); return rc; }
+            }
+            s->weight_bytes += (int64_t)(an.nbytes + fn.nbytes + wq.nbytes + wk.nbytes + wv.nbytes + wo.nbytes + w1.nbytes + w2.nbytes + w3.nbytes);
+        }
+    } catch (const std::exception & e) {
+        if (scratch) cudaFree(scratch);
+        return fail(B200_EFILE, "error loading model: %s", e.what());
+    }
+    cudaFree(scratch);
+
+    const size_t nE = (size_t) s->n_ctx * E;
+    if ((rc = dev_alloc(s, &s->kc, (size_t) s->L * nE)) || (rc = dev_alloc(s, &s->vc, (size_t) s->L * nE)) ||
+        (rc = dev_alloc(s, &s->q16, nE)) || (rc = dev_alloc(s, &s->xa, nE)) || (rc = dev_alloc(s, &s->xb, nE)) ||
+        (rc = dev_alloc(s, &s->qkv, 3 * nE)) || (rc = dev_alloc(s, &s->att, nE)) || (rc = dev_alloc(s, &s->ffin, nE)) ||
+        (rc = dev_alloc(s, &s->gate, (size_t) s->n_ctx * FF)) || (rc = dev_alloc(s, &s->d_in, nE)) ||
+        (rc = dev_alloc(s, &s->d_out, nE)) || (rc = dev_alloc(s, &s->d_npast, 1)))
+        return rc;
+    B200_CUDA(cudaMemset(s->kc, 0, (size_t) s->L * nE * 2));
+    B200_CUDA(cudaMemset(s->vc, 0, (size_t) s->L * nE * 2));
+    B200_CUDA(cudaMemset(s->d_npast, 0, 4));
+    B200_CUDA(cudaMallocHost((void **) &s->h_in, (size_t) E * 4));
+    B200_CUDA(cudaMallocHost((void **) &s->h_out, (size_t) E * 4));
+    if ((rc = build_tables(s))) return rc;
+    B200_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    B200_CUDA(cudaEventCreate(&s->ev0));
+    B200_CUDA(cudaEventCreate(&s->ev1));
+    B200_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+static void destroy(b200_slice * s) {
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto & kv : s->graphs) cudaGraphExecDestroy(kv.second);
+    for (void * p : s->allocs) cudaFree(p);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+}  // namespace b200
+
+// ============================================================================ C ABI
+extern "C" {
+
+const char * b200_last_error(void) { return b200::last_error_ref().c_str(); }
+const char * b200_version(void) { return "b200-slice 0.1 (sm_100a, exact mode)"; }
+
+int b200_slice_load(const char * path, int device, int n_ctx, b200_slice_t ** out) {
+    if (!path || !out) return fail(B200_EINVAL, "b200_slice_load: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(B200_ENODEV, "no CUDA device visible: the slice forward has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200_ENODEV, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(B200_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    B200_CUDA(cudaSetDevice(device));
+    b200_slice * s = new b200_slice();
+    s->device = device; s->n_sm = prop.multiProcessorCount;
+    s->n_ctx = n_ctx > 0 ? n_ctx : 512;               // vendor examples/common.h:28
+    s->use_ring  = env_int("B200_RING", 1) != 0;
+    s->use_graph = env_int("B200_GRAPH", 1) != 0;
+    s->use_pdl   = env_int("B200_PDL", 0) != 0;
+    s->opt_ns = env_int("B200_NS", 0); s->opt_qs = env_int("B200_QS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0);
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete s; return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+    int rc = load_locked(s, path);
+    if (rc) { destroy(s); return rc; }
+    *out = s;
+    return 0;
+}
+
+int b200_slice_unload(b200_slice_t * s) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    destroy(s);
+    return 0;
+}
+
+int b200_slice_clear(b200_slice_t * s) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaMemsetAsync(s->d_npast, 0, 4, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    s->n_past = 0;
+    return 0;
+}
+
+int b200_slice_rewind(b200_slice_t * s, int n_past) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (n_past < 0 || n_past > s->n_past) return fail(B200_EINVAL, "rewind target %d outside [0, %d]", n_past, s->n_past);
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaMemcpyAsync(s->d_npast, &n_past, 4, cudaMemcpyHostToDevice, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    s->n_past = n_past;
+    return 0;
+}
+
+int b200_slice_info(b200_slice_t * s, b200_slice_info_t * info) {
+    if (!s || !info) return fail(B200_EINVAL, "null argument");
+    info->n_embd = s->E; info->n_head = s->H; info->n_ff = s->FF; info->n_layer = s->L; info->first_layer = s->first_layer;
+    info->n_ctx = s->n_ctx; info->n_past = s->n_past; info->weight_type = s->wtype; info->device = s->device;
+    info->weight_bytes = s->weight_bytes; info->kv_bytes_per_pos = (int64_t) s->L * 2 * s->E * 2;
+    return 0;
+}
+
+int b200_slice_forward(b200_slice_t * s, const float * in, int n_tokens, float * out) {
+    if (!s || !in || !out) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return forward_locked(s, in, n_tokens, out, true);
+}
+
+int b200_slice_forward_device(b200_slice_t * s, const float * d_in, int n_tokens, float * d_out, int sync) {
+    if (!s || !d_in || !d_out) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = forward_locked(s, d_in, n_tokens, d_out, false);
+    if (rc) return rc;
+    if (sync) B200_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int b200_slice_sync(b200_slice_t * s) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+float b200_slice_last_ms(b200_slice_t * s) {
+    if (!s || !s->timed) return -1.f;
+    float ms = -1.f;
+    cudaSetDevice(s->device);
+    if (cudaEventSynchronize(s->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+int64_t b200_slice_launch_count(b200_slice_t * s) { return s ? s->launches : 0; }
+float * b200_slice_dev_in(b200_slice_t * s)  { return s ? s->d_in : nullptr; }
+float * b200_slice_dev_out(b200_slice_t * s) { return s ? s->d_out : nullptr; }
+
+/* Test hook: copy `count` 32-bit words of an internal activation buffer to the host after a
+ * forward (0 qkv, 1 att, 2 ffin, 3 gate, 4 xa, 5 xb, 6 q16, 7 k-cache, 8 v-cache). */
+int b200_debug_read(b200_slice_t * s, int which, size_t offset_words, size_t count, void * out) {
+    if (!s || !out) return fail(B200_EINVAL, "null argument");
+    const void * src[9] = {s->qkv, s->att, s->ffin, s->gate, s->xa, s->xb, s->q16, s->kc, s->vc};
+    if (which < 0 || which > 8) return fail(B200_EINVAL, "bad buffer id %d", which);
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    B200_CUDA(cudaMemcpy(out, (const uint32_t *) src[which] + offset_words, count * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

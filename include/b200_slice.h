@@ -1,0 +1,138 @@
+/*
+ * b200_slice.h -- C ABI of libb200slice.so, the B200 (sm_100a) slice runtime.
+ *
+ * Drop-in boundary: these entry points are what the reference's CPython module `llm`
+ * (distllm/tensor_processor.cpp:2238-2260) binds for the per-slice forward path, with Python
+ * lists replaced by plain float buffers.  Each function cites the reference interface it
+ * replaces.  Conventions:
+ *   - return 0 on success, a B200_E* code otherwise; no C++ exception crosses the ABI;
+ *     b200_last_error() returns a thread-local, human-readable description of the last failure;
+ *   - the caller owns every in/out buffer (they are copied, as the reference copies at
+ *     tensor_processor.cpp:523 and 798-799); the library owns weights, KV cache and n_past;
+ *   - activations are row-major [n_tokens][n_embd] float32 (ggml ne0 = n_embd);
+ *   - one handle = one slice on one GPU; calls on a handle are serialised by an internal mutex;
+ *   - there is NO CPU fallback: every call fails with B200_ENODEV when no sm_100 device is present.
+ */
+#ifndef B200_SLICE_H
+#define B200_SLICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_slice b200_slice_t;
+typedef struct b200_extra b200_extra_t;
+
+enum {
+    B200_OK       = 0,
+    B200_EINVAL   = 1,   /* bad argument (null handle, n_tokens <= 0, ...) */
+    B200_EFILE    = 2,   /* slice file missing / malformed / unsupported tensor type */
+    B200_ENODEV   = 3,   /* no CUDA device, or device is not sm_100 */
+    B200_ECUDA    = 4,   /* a CUDA call or kernel failed */
+    B200_ECONTEXT = 5,   /* n_past + n_tokens would exceed n_ctx */
+    B200_ENCCL    = 6,   /* pipeline hand-off failed */
+};
+
+typedef struct b200_slice_info {
+    int32_t n_embd, n_head, n_ff, n_layer, first_layer, n_ctx, n_past, weight_type, device;
+    int64_t weight_bytes;       /* bytes of slice weights as stored in the reference file */
+    int64_t kv_bytes_per_pos;   /* KV-cache bytes appended per position (all layers) */
+} b200_slice_info_t;
+
+/* ---- slice lifetime ------------------------------------------------------------------ */
+
+/* llm.load_slice(path)  (tensor_processor.cpp:1995-2009; TransformerSlice ctor 1497-1510).
+ * Parses the reference's slice file (GGJT v3 + first_layer, tensor_processor.cpp:152-248),
+ * uploads and repacks the weights into HBM, allocates the f16 KV cache for n_ctx positions.
+ * n_ctx <= 0 selects the reference default, 512 (vendor examples/common.h:28). */
+int b200_slice_load(const char * path, int device, int n_ctx, b200_slice_t ** out);
+
+/* llm.unload_slice()  (tensor_processor.cpp:2023-2030). */
+int b200_slice_unload(b200_slice_t * s);
+
+/* llm.clear_context()  (tensor_processor.cpp:2012-2021, TransformerSlice::clear_context 1512-1521):
+ * n_past = 0; the cache contents become unreachable. */
+int b200_slice_clear(b200_slice_t * s);
+
+int b200_slice_info(b200_slice_t * s, b200_slice_info_t * info);
+
+/* Extension (no reference counterpart): move n_past back to `n_past` (<= current) so a benchmark
+ * can re-decode positions without re-running the prefill.  Cache rows below n_past stay valid. */
+int b200_slice_rewind(b200_slice_t * s, int n_past);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+
+/* llm.propagate_forward(values)  (tensor_processor.cpp:2127-2163 -> TransformerSlice::forward
+ * 1523-1544 -> llama_eval_internal 474-809).  `in` and `out` are HOST buffers of
+ * n_tokens*n_embd floats; the call copies in (H2D), runs every layer of the slice on the GPU at
+ * positions [n_past, n_past+n_tokens), copies out (D2H), and advances n_past. */
+int b200_slice_forward(b200_slice_t * s, const float * in, int n_tokens, float * out);
+
+/* Same, with DEVICE buffers on the slice's GPU; asynchronous on the slice's stream unless
+ * `sync` != 0.  Used when the activation already lives in HBM (chained slices, benchmarks). */
+int b200_slice_forward_device(b200_slice_t * s, const float * d_in, int n_tokens, float * d_out, int sync);
+
+/* Block until everything queued on the slice's stream has finished. */
+int b200_slice_sync(b200_slice_t * s);
+
+/* Device-side time of the kernels launched by the most recent forward call, in milliseconds
+ * (CUDA events on the slice's stream); -1 if none. */
+float b200_slice_last_ms(b200_slice_t * s);
+
+/* Number of kernel launches (graph nodes included) issued by this handle so far. */
+int64_t b200_slice_launch_count(b200_slice_t * s);
+
+/* Device pointers of the slice's own input / output staging buffers ([n_ctx][n_embd] f32). */
+float * b200_slice_dev_in(b200_slice_t * s);
+float * b200_slice_dev_out(b200_slice_t * s);
+
+/* Test hook: copy `count` 32-bit words of an internal activation buffer to the host after a forward
+ * (0 qkv, 1 att, 2 ffin, 3 gate, 4 xa, 5 xb, 6 q16, 7 k-cache, 8 v-cache).  Not part of the drop-in surface. */
+int b200_debug_read(b200_slice_t * s, int which, size_t offset_words, size_t count, void * out);
+
+/* ---- layer-slice pipeline over NVLink (one process per GPU) --------------------------- */
+
+/* Join a pipeline of `nranks` slices (rank r holds layer range r of the nodes_map).  `nccl_id`
+ * is the 128-byte ncclUniqueId obtained with b200_pipeline_unique_id on rank 0 and distributed
+ * by the host (torch.distributed store / TCP).  Replaces the client relaying the activation over
+ * TCP between nodes (cli_api/common.py:148-154, control_center.py:224-244) for slices that share
+ * one NVSwitch box: the hand-off becomes ONE ncclSend/ncclRecv per hop. */
+int b200_pipeline_unique_id(void * id128);
+int b200_pipeline_init(b200_slice_t * s, int rank, int nranks, const void * id128);
+
+/* One pipeline step on this rank: rank 0 takes `d_in` (device, may be NULL on other ranks), every
+ * rank r>0 receives [n_tokens][n_embd] from r-1, runs its layers, and sends to r+1; the last rank
+ * leaves the result in its dev_out buffer and, when `ring` != 0, also sends it to rank 0 (which
+ * receives it into its dev_out), closing the token loop. Asynchronous on the slice's stream. */
+int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int ring);
+int b200_pipeline_destroy(b200_slice_t * s);
+
+/* ---- client-side extra layers (tok_embeddings / norm / output), next-row N1 ------------ */
+
+/* Replace get_inputs / get_llm_output / sample_next_token (tensor_processor.cpp:1717-1908),
+ * which re-read the extra-layers file on every call, with a resident copy. */
+int b200_extra_load(const char * path, int device, b200_extra_t ** out);
+int b200_extra_unload(b200_extra_t * e);
+int b200_extra_dims(b200_extra_t * e, int * n_vocab, int * n_embd);
+/* llm.prepare_embeddings(path, tokens) -> [n_tokens][n_embd] (host). */
+int b200_extra_embed(b200_extra_t * e, const int32_t * tokens, int n_tokens, float * out);
+/* llm.get_logits(path, emb, all_logits) -> [n_tokens or 1][n_vocab] (host). */
+int b200_extra_logits(b200_extra_t * e, const float * emb, int n_tokens, int all_logits, float * out);
+/* llm.get_next_token(path, emb): argmax of the last token's logits (first maximum wins). */
+int b200_extra_next_token(b200_extra_t * e, const float * emb, int n_tokens, int32_t * token);
+/* llm.tokenize_prompt(path, prompt): BOS + sentencepiece-style merge (tensor_processor.cpp:1596-1714).
+ * Returns the token count (may exceed cap; only cap are written) or a negative error. */
+int b200_extra_tokenize(b200_extra_t * e, const char * prompt, int32_t * out, int cap);
+/* llm.decode_token(path, id): pointer to the token's bytes (owned by the handle), length in *len. */
+const char * b200_extra_token_text(b200_extra_t * e, int32_t id, int * len);
+
+const char * b200_last_error(void);
+const char * b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SLICE_H */
