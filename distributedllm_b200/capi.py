@@ -51,6 +51,12 @@ def lib() -> C.CDLL:
         L.b200_slice_last_ms.restype = cf
         L.b200_slice_launch_count.argtypes = [vp]
         L.b200_slice_launch_count.restype = C.c_int64
+        L.b200_slice_mark.argtypes = [vp, ci]
+        L.b200_slice_mark_elapsed_ms.argtypes = [vp]
+        L.b200_slice_mark_elapsed_ms.restype = cf
+        L.b200_slice_profile.argtypes = [vp, ci]
+        L.b200_slice_profile_read.argtypes = [vp, vp, vp, ci]
+        L.b200_debug_read.argtypes = [vp, ci, C.c_size_t, C.c_size_t, vp]
         L.b200_slice_dev_in.argtypes = [vp]
         L.b200_slice_dev_in.restype = vp
         L.b200_slice_dev_out.argtypes = [vp]
@@ -131,6 +137,26 @@ class Slice:
     @property
     def dev_out(self) -> int:
         return lib().b200_slice_dev_out(self._h)
+
+    def mark(self, which: int) -> None:
+        check(lib().b200_slice_mark(self._h, which))
+
+    def mark_elapsed_ms(self) -> float:
+        return float(lib().b200_slice_mark_elapsed_ms(self._h))
+
+    def profile(self, enable: bool) -> None:
+        check(lib().b200_slice_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        ms = np.zeros(7, np.float32)
+        cnt = np.zeros(7, np.int32)
+        check(lib().b200_slice_profile_read(self._h, _ptr(ms), _ptr(cnt), 7))
+        return ms, cnt
+
+    def debug_read(self, which: int, count: int, dtype=np.float32) -> np.ndarray:
+        out = np.zeros(count, np.uint32)
+        check(lib().b200_debug_read(self._h, which, 0, count, _ptr(out)))
+        return out.view(dtype)
 
     def last_ms(self) -> float:
         return float(lib().b200_slice_last_ms(self._h))

@@ -33,6 +33,7 @@ constexpr int kWT_F16 = 1, kWT_Q4_0 = 2, kWT_Q8_0 = 8;
 constexpr int kQ4Chunk = 576, kQ8Chunk = 1088;
 constexpr int kWPC = 4;                 // consumer warps per CTA (8 rows x G groups each)
 constexpr int kConsumers = kWPC * 32;
+constexpr int kQS = 4;                  // quads per ring stage (nbq is padded to a multiple of kQS at pack time)
 constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: int->float through the dp4a accumulator
 constexpr int kMagicI = 0x4B400000;
 
@@ -129,23 +130,61 @@ __global__ void k_repack(RepackArgs a) {
 //     shared memory in dp4a word order
 //   * epilogue (fused): store | + residual | SiLU(w1 x) * (w3 x)
 // =============================================================================================
-enum { PRO_PLAIN = 0, PRO_NORM = 1 };
-enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GATE = 2 };
+enum { PRO_PLAIN = 0, PRO_NORM = 1, PRO_PREQ = 2 };
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GATE = 2, EPI_GATEQ = 3 };
 
 struct GemvArgs {
     PackedW W;
-    const float * x;      int ldx;       // input  [N][ldx], K valid per row
+    const float * x;      int ldx;       // PRO_PLAIN / PRO_NORM: input [N][ldx], K valid per row
     const float * norm_w;                // PRO_NORM: weight [K]
+    const int * aq_in; const float * da_in;   // PRO_PREQ: pre-quantised input, [N][nbq*32] words + [N][nbq*4] scales
     const float * resid;  int ldr;       // EPI_RESID
     float * y;            int ldy;       // output [N][ldy]
+    int * aq_out; float * da_out; int out_nbq; float out_dscale;   // EPI_GATEQ: quantised output for the next matmul
     int N;                               // columns (tokens)
     int out_rows;                        // valid output rows (E, 3E, or FF for the gate)
-    const uint16_t * tsilu;              // EPI_GATE: fp16 SiLU table (65536 entries)
-    int QS;                              // quads per ring stage
+    const uint16_t * tsilu;              // EPI_GATE*: fp16 SiLU table (65536 entries)
     int NS;                              // ring stages
 };
 
 __host__ __device__ inline size_t act_bytes_per_col(int nbq) { return (size_t) nbq * (128 + 16); }
+
+// Q8_0 act-quant (ggml.c:1215-1252) of the 32 values held one per lane, written straight into the
+// dp4a word layout the matmul consumers read: words [Q][w&3][bq][w>>2], scale [b] (x dscale).
+__device__ __forceinline__ void warp_quant_block(float v, int lane, int * aq_col, float * da_col, int b, float dscale) {
+    float amax = fabsf(v);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
+    const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
+    uint32_t pk = ((uint32_t)(__float2int_rn(fmul(v, id)) & 0xFF)) << (8 * (lane & 3));
+    pk |= __shfl_xor_sync(0xffffffffu, pk, 1);
+    pk |= __shfl_xor_sync(0xffffffffu, pk, 2);
+    if ((lane & 3) == 0) {
+        const int w = lane >> 2;
+        aq_col[(b >> 2) * 32 + (w & 3) * 8 + (b & 3) * 2 + (w >> 2)] = (int) pk;
+    }
+    if (lane == 0) da_col[b] = fmul(d, dscale);
+}
+
+// quantise one 32-float block held in registers by ONE thread into shared memory
+template <int WT>
+__device__ __forceinline__ void thread_quant_block(const float (&v)[32], int * an, float * dn, int b) {
+    float amax = 0.f;
+    #pragma unroll
+    for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
+    const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
+    const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
+    dn[b] = (WT == kWT_Q4_0) ? fmul(d, 0.0625f) : d;        // the 1/16 of the nibble placement, folded (exact)
+    int * dst = an + (b >> 2) * 32 + (b & 3) * 2;
+    #pragma unroll
+    for (int w = 0; w < 8; w++) {
+        uint32_t pk = 0;
+        #pragma unroll
+        for (int j = 0; j < 4; j++) pk |= ((uint32_t)(__float2int_rn(fmul(v[w*4 + j], id)) & 0xFF)) << (8 * j);
+        dst[(w & 3) * 8 + (w >> 2)] = (int) pk;
+    }
+}
 
 template <int WT, int G, int NC, int PRO, int EPI, bool RING>
 __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
@@ -153,42 +192,41 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
     constexpr int TR = kWPC * G;
     extern __shared__ __align__(128) uint8_t smem[];
     const int nbq = a.W.nbq, K = a.W.K, nb = a.W.nb;
-    const int QS = a.QS, NS = a.NS;
-    const int stage_bytes = QS * TR * CB;
-    // smem carve-up: [ring NS*stage_bytes][act words NC*nbq*128][act scales NC*nbq*16][barriers][scratch]
+    const int NS = a.NS;
+    constexpr int stage_bytes = kQS * TR * CB;
+    // smem: [ring NS*stage][act words NC*nbq*128][act scales NC*nbq*16][full 16][empty 16][act bar][red 4][gq NC*32]
     uint8_t * ring = smem;
     int * a_s = (int *)(smem + (RING ? (size_t) NS * stage_bytes : 0));
     float * da_s = (float *)((uint8_t *) a_s + (size_t) NC * nbq * 128);
     uint64_t * full = (uint64_t *)((uint8_t *) da_s + (size_t) NC * nbq * 16);
     uint64_t * empty = full + 16;
-    double * red = (double *)(empty + 16);           // [kWPC] reduction scratch
+    uint64_t * actbar = empty + 16;
+    double * red = (double *)(actbar + 2);           // [kWPC]
+    float * gq = (float *)(red + kWPC);              // [NC][32] gate values of one tile (EPI_GATEQ)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int col0 = blockIdx.y * NC;
-    const int n_stage = (nbq + QS - 1) / QS;
+    const int n_stage = nbq / kQS;
 
-    if (RING) {
-        if (tid == 0) {
-            for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWPC); }
-            mbar_fence_init();
-        }
-        __syncthreads();
+    if (tid == 0) {
+        if (RING) for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWPC); }
+        mbar_init(actbar, 1);
+        mbar_fence_init();
     }
+    __syncthreads();
 
     if (RING && warp == kWPC) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
             grid_dep_launch();
-            int it = 0;
+            int slot = 0, use = 0;
             for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
                 const uint8_t * src = a.W.data + (long long) tile * a.W.tile_bytes;
-                for (int s = 0; s < n_stage; s++, it++) {
-                    const int slot = it % NS, use = it / NS;
+                for (int s = 0; s < n_stage; s++) {
                     if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
-                    const int q0 = s * QS, qn = min(QS, nbq - q0);
-                    const uint32_t bytes = (uint32_t) qn * TR * CB;
-                    mbar_arrive_expect_tx(&full[slot], bytes);
-                    bulk_g2s(ring + (size_t) slot * stage_bytes, src + (size_t) q0 * TR * CB, bytes, &full[slot]);
+                    mbar_arrive_expect_tx(&full[slot], (uint32_t) stage_bytes);
+                    bulk_g2s(ring + (size_t) slot * stage_bytes, src + (size_t) s * stage_bytes, (uint32_t) stage_bytes, &full[slot]);
+                    if (++slot == NS) { slot = 0; use++; }
                 }
             }
         }
@@ -197,77 +235,99 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
 
     // ---------------------------------------------------------------------- consumer warps
     if (!RING && tid == 0) grid_dep_launch();
-    grid_dep_wait();                                   // input x comes from the previous kernel
+    grid_dep_wait();                                   // the input comes from the previous kernel
 
-    // prologue: (norm +) quantise NC input columns into shared memory
-    for (int n = 0; n < NC; n++) {
-        const int col = col0 + n;
-        int * an = a_s + (size_t) n * nbq * 32;
-        float * dn = da_s + (size_t) n * nbq * 4;
-        if (col >= a.N) {                              // padded column: zeros
-            for (int i = tid; i < nbq * 32; i += kConsumers) an[i] = 0;
-            for (int i = tid; i < nbq * 4; i += kConsumers) dn[i] = 0.f;
-            continue;
+    const int ncols = min(NC, a.N - col0);
+    if (PRO == PRO_PREQ) {
+        // the producer of the activation already quantised it (attention / gate epilogue): two bulk copies
+        if (tid == 0) {
+            const uint32_t b1 = (uint32_t) ncols * nbq * 128, b2 = (uint32_t) ncols * nbq * 16;
+            mbar_arrive_expect_tx(actbar, b1 + b2);
+            bulk_g2s(a_s, a.aq_in + (size_t) col0 * nbq * 32, b1, actbar);
+            bulk_g2s(da_s, a.da_in + (size_t) col0 * nbq * 4, b2, actbar);
         }
-        const float * x = a.x + (size_t) col * a.ldx;
-        float scale = 1.0f;
-        if (PRO == PRO_NORM) {
-            double s = 0.0;
-            for (int i = tid * 4; i < K; i += kConsumers * 4) {
-                const float4 v = *(const float4 *)(x + i);
-                s += (double) fmul(v.x, v.x); s += (double) fmul(v.y, v.y);
-                s += (double) fmul(v.z, v.z); s += (double) fmul(v.w, v.w);
-            }
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) red[warp] = s;
-            named_bar_sync(1, kConsumers);
-            const double tot = (red[0] + red[1]) + (red[2] + red[3]);
-            named_bar_sync(1, kConsumers);
-            const float mean = (float)(tot / (double) K);
-            scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd(mean, 1e-6f)));
+        for (int n = ncols; n < NC; n++) {
+            for (int i = tid; i < nbq * 32; i += kConsumers) a_s[(size_t) n * nbq * 32 + i] = 0;
+            for (int i = tid; i < nbq * 4; i += kConsumers) da_s[(size_t) n * nbq * 4 + i] = 0.f;
         }
-        for (int b = tid; b < nbq * 4; b += kConsumers) {
-            const int Q = b >> 2, bq = b & 3;
-            int * dst = an + Q * 32 + bq * 2;          // [Q][w][bq][2]: + w*8 per word pair
-            if (b >= nb) {
-                for (int w = 0; w < 4; w++) { dst[w * 8] = 0; dst[w * 8 + 1] = 0; }
-                dn[b] = 0.f;
+        mbar_wait(actbar, 0);
+    } else {
+        for (int n = 0; n < NC; n++) {
+            int * an = a_s + (size_t) n * nbq * 32;
+            float * dn = da_s + (size_t) n * nbq * 4;
+            if (n >= ncols) {                              // padded column: zeros
+                for (int i = tid; i < nbq * 32; i += kConsumers) an[i] = 0;
+                for (int i = tid; i < nbq * 4; i += kConsumers) dn[i] = 0.f;
                 continue;
             }
-            float v[32];
-            #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                float4 t = *(const float4 *)(x + b * 32 + j * 4);
-                if (PRO == PRO_NORM) {
-                    const float4 wv = *(const float4 *)(a.norm_w + b * 32 + j * 4);
-                    t.x = fmul(fmul(t.x, scale), wv.x); t.y = fmul(fmul(t.y, scale), wv.y);
-                    t.z = fmul(fmul(t.z, scale), wv.z); t.w = fmul(fmul(t.w, scale), wv.w);
-                }
-                v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
+            const float * x = a.x + (size_t)(col0 + n) * a.ldx;
+            for (int b = nb + tid; b < nbq * 4; b += kConsumers) {       // padding blocks
+                int * dst = an + (b >> 2) * 32 + (b & 3) * 2;
+                for (int w = 0; w < 4; w++) { dst[w * 8] = 0; dst[w * 8 + 1] = 0; }
+                dn[b] = 0.f;
             }
-            float amax = 0.f;
-            #pragma unroll
-            for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
-            const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
-            const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
-            // Q4_0 path folds the 1/16 of the nibble placement into the activation scale (exact)
-            dn[b] = (WT == kWT_Q4_0) ? fmul(d, 0.0625f) : d;
-            #pragma unroll
-            for (int w = 0; w < 8; w++) {
-                uint32_t pk = 0;
+            if (PRO == PRO_NORM && nb <= kConsumers) {
+                // one global round trip: x block and norm weights in flight together, x kept in registers
+                float v[32], wn[32];
+                const bool own = tid < nb;
                 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int qv = __float2int_rn(fmul(v[w*4 + j], id));
-                    pk |= ((uint32_t)(qv & 0xFF)) << (8 * j);
+                for (int j = 0; j < 8; j++) {
+                    const float4 t = own ? *(const float4 *)(x + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 u = own ? *(const float4 *)(a.norm_w + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
+                    wn[j*4] = u.x; wn[j*4+1] = u.y; wn[j*4+2] = u.z; wn[j*4+3] = u.w;
                 }
-                dst[(w & 3) * 8 + (w >> 2)] = (int) pk;
+                double s = 0.0;
+                #pragma unroll
+                for (int j = 0; j < 32; j++) s += (double) fmul(v[j], v[j]);
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) red[warp] = s;
+                named_bar_sync(1, kConsumers);
+                const double tot = (red[0] + red[1]) + (red[2] + red[3]);
+                named_bar_sync(1, kConsumers);
+                const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) K), 1e-6f)));
+                if (own) {
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = fmul(fmul(v[j], scale), wn[j]);
+                    thread_quant_block<WT>(v, an, dn, tid);
+                }
+            } else {
+                float scale = 1.0f;
+                if (PRO == PRO_NORM) {
+                    double s = 0.0;
+                    for (int i = tid * 4; i < K; i += kConsumers * 4) {
+                        const float4 v = *(const float4 *)(x + i);
+                        s += (double) fmul(v.x, v.x); s += (double) fmul(v.y, v.y);
+                        s += (double) fmul(v.z, v.z); s += (double) fmul(v.w, v.w);
+                    }
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) red[warp] = s;
+                    named_bar_sync(1, kConsumers);
+                    const double tot = (red[0] + red[1]) + (red[2] + red[3]);
+                    named_bar_sync(1, kConsumers);
+                    scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) K), 1e-6f)));
+                }
+                for (int b = tid; b < nb; b += kConsumers) {
+                    float v[32];
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 t = *(const float4 *)(x + b * 32 + j * 4);
+                        if (PRO == PRO_NORM) {
+                            const float4 wv = *(const float4 *)(a.norm_w + b * 32 + j * 4);
+                            t.x = fmul(fmul(t.x, scale), wv.x); t.y = fmul(fmul(t.y, scale), wv.y);
+                            t.z = fmul(fmul(t.z, scale), wv.z); t.w = fmul(fmul(t.w, scale), wv.w);
+                        }
+                        v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
+                    }
+                    thread_quant_block<WT>(v, an, dn, b);
+                }
             }
         }
     }
     named_bar_sync(1, kConsumers);
 
     const int r = lane >> 2, w = lane & 3;
-    int it = 0;
+    int slot = 0, phase = 0;
     for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
         float acc[G][NC][2];
         #pragma unroll
@@ -276,23 +336,22 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             for (int n = 0; n < NC; n++) { acc[g][n][0] = 0.f; acc[g][n][1] = 0.f; }
         const uint8_t * gsrc = a.W.data + (long long) tile * a.W.tile_bytes;
 
-        for (int s = 0; s < n_stage; s++, it++) {
-            const int q0 = s * QS, qn = min(QS, nbq - q0);
+        for (int s = 0; s < n_stage; s++) {
             const uint8_t * base;
-            int slot = 0;
             if (RING) {
-                slot = it % NS;
-                mbar_wait(&full[slot], (it / NS) & 1);
+                mbar_wait(&full[slot], phase);
                 base = ring + (size_t) slot * stage_bytes;
             } else {
-                base = gsrc + (size_t) q0 * TR * CB;
+                base = gsrc + (size_t) s * stage_bytes;
             }
-            for (int qi = 0; qi < qn; qi++) {
-                const int Q = q0 + qi;
+            base += (size_t)(warp * G) * CB;
+            #pragma unroll
+            for (int qi = 0; qi < kQS; qi++) {
+                const int Q = s * kQS + qi;
                 uint4 wv[G], wv2[G]; uint2 sc[G];
                 #pragma unroll
                 for (int g = 0; g < G; g++) {
-                    const uint8_t * ch = base + (size_t)(qi * TR + warp * G + g) * CB;
+                    const uint8_t * ch = base + (size_t)(qi * TR + g) * CB;
                     wv[g] = *(const uint4 *)(ch + lane * 16);
                     if (WT == kWT_Q8_0) { wv2[g] = *(const uint4 *)(ch + 512 + lane * 16); sc[g] = *(const uint2 *)(ch + 1024 + r * 8); }
                     else sc[g] = *(const uint2 *)(ch + 512 + r * 8);
@@ -325,7 +384,11 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                     }
                 }
             }
-            if (RING) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[slot]); }
+            if (RING) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+                if (++slot == NS) { slot = 0; phase ^= 1; }
+            }
         }
 
         // epilogue: hsum_float_8 order ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7))
@@ -339,32 +402,35 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 1));
                 res[g][n] = t;
             }
-        if (w == 0) {
-            if (EPI == EPI_GATE) {
-                const int row = (tile * kWPC + warp) * 8 + r;
+        if (EPI == EPI_GATE || EPI == EPI_GATEQ) {
+            const int row = (tile * kWPC + warp) * 8 + r;
+            if (w == 0) {
+                #pragma unroll
+                for (int n = 0; n < NC; n++) {
+                    const float gv = fmul(h2f(a.tsilu[f2h(res[0][n])]), res[G - 1][n]);
+                    if (EPI == EPI_GATEQ) gq[n * 32 + warp * 8 + r] = row < a.out_rows ? gv : 0.f;
+                    else if (row < a.out_rows && n < ncols) a.y[(size_t)(col0 + n) * a.ldy + row] = gv;
+                }
+            }
+            if (EPI == EPI_GATEQ) {
+                // the tile's 32 gate rows are exactly one Q8_0 block of w2's input: quantise it here
+                named_bar_sync(1, kConsumers);
+                for (int n = warp; n < ncols; n += kWPC)
+                    warp_quant_block(gq[n * 32 + lane], lane, a.aq_out + (size_t)(col0 + n) * a.out_nbq * 32,
+                                     a.da_out + (size_t)(col0 + n) * a.out_nbq * 4, tile, a.out_dscale);
+                named_bar_sync(1, kConsumers);
+            }
+        } else if (w == 0) {
+            #pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int row = ((tile * kWPC + warp) * G + g) * 8 + r;
                 if (row < a.out_rows) {
                     #pragma unroll
                     for (int n = 0; n < NC; n++) {
-                        const int col = col0 + n;
-                        if (col < a.N) {
-                            const float sl = h2f(a.tsilu[f2h(res[0][n])]);
-                            a.y[(size_t) col * a.ldy + row] = fmul(sl, res[G - 1][n]);
-                        }
-                    }
-                }
-            } else {
-                #pragma unroll
-                for (int g = 0; g < G; g++) {
-                    const int row = ((tile * kWPC + warp) * G + g) * 8 + r;
-                    if (row < a.out_rows) {
-                        #pragma unroll
-                        for (int n = 0; n < NC; n++) {
-                            const int col = col0 + n;
-                            if (col < a.N) {
-                                float v = res[g][n];
-                                if (EPI == EPI_RESID) v = fadd(v, a.resid[(size_t) col * a.ldr + row]);
-                                a.y[(size_t) col * a.ldy + row] = v;
-                            }
+                        if (n < ncols) {
+                            float v = res[g][n];
+                            if (EPI == EPI_RESID) v = fadd(v, a.resid[(size_t)(col0 + n) * a.ldr + row]);
+                            a.y[(size_t)(col0 + n) * a.ldy + row] = v;
                         }
                     }
                 }
@@ -608,6 +674,192 @@ __global__ void __launch_bounds__(512) k_attention(const AttnArgs a) {
         const uint16_t * v = a.vc + h * D + tid;
         for (int t = npT; t < tcount; t++) sumf += (double) fmul(h2f(v[(size_t) t * E]), h2f(p16[t]));
         a.out[(size_t) n * E + h * D + tid] = (float) sumf;
+    }
+}
+
+// =============================================================================================
+// K5c: attention for head size 128, one thread-block CLUSTER of 4 CTAs per (head, query token).
+// Same arithmetic as k_attention; the work is cut along the structure ggml_vec_dot_f16 already has:
+//   * V.p keeps 32 f32 slots per channel, slot = t mod 32, and the AVX reduce first adds the four
+//     8-lane vectors j = slot/8.  CTA g of the cluster owns vector j = g, i.e. positions
+//     t = 32k + 8g + l (l = 0..7): it computes THOSE scores and accumulates THOSE slots, so K and V
+//     are each read exactly once per step and 4x as many SMs pull on HBM/L2 per head.
+//   * scores and slot partials meet through a small global scratch (L2-resident) ordered by
+//     barrier.cluster release/acquire; every CTA then runs the (cheap) softmax redundantly and CTA g
+//     finishes channels [32g, 32g+32) with the fixed reduce tree and the double-precision tail.
+// FUSE (decode, N = 1): RoPE of q and k, fp16 rounding and the KV append of the new position are
+// done in the prologue from the f32 qkv row, removing the separate rope/append launch.
+// K.q: 4 lanes per position, lane ql loads the four 16 B vectors m = ql + 4c (c = chunk) and owns
+// slots 8*ql + e, so each 256 B key row is one coalesced 64 B segment per chunk.
+// =============================================================================================
+struct Attn128Args {
+    const float * qkv;            // FUSE: [N][3E] f32 (q | k | v), pre-RoPE
+    const uint16_t * q16;         // !FUSE: [N][E] fp16 bits, post-RoPE
+    uint16_t * kc; uint16_t * vc; // this layer's cache [n_ctx][E]
+    const int * n_past; int E, H, N, n0;   // n0: first query token of this launch (chunked prefill launches)
+    const float2 * cs; const uint16_t * texp;
+    float * out;                  // [N][E]
+    int * aq_out; float * da_out; int out_nbq; float out_dscale;   // optional: Q8_0-quantised output for the wo matmul
+    float * sc_scratch;           // [chunk][H][n_ctx]
+    float * part_scratch;         // [chunk][H][4][8][128]
+    int n_ctx; float kq_scale;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool FUSE>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const Attn128Args a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(16) uint16_t q16s[128], k16s[128], v16s[128];
+    __shared__ double redd[8]; __shared__ float redf[8];
+    if (threadIdx.x == 0) grid_dep_launch();
+    grid_dep_wait();
+    const int h = blockIdx.x >> 2, g = blockIdx.x & 3, ny = blockIdx.y, n = a.n0 + ny, E = a.E;
+    const int n_past = *a.n_past, T = n_past + a.N, tcount = n_past + n + 1, pos = n_past + n;
+    float * sc = (float *) smem;                                   // [T]
+    uint16_t * p16 = (uint16_t *)(sc + ((T + 3) & ~3));            // [T]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint16_t * kc = a.kc, * vc = a.vc;
+
+    // ---- phase 0: q (and, fused, the new k / v row) into shared memory
+    if (FUSE) {
+        if (tid < 64) {
+            const float * row = a.qkv + (size_t) n * 3 * E + h * 128;
+            const float2 cs = a.cs[(size_t) pos * 64 + tid];
+            const float2 q = *(const float2 *)(row + 2 * tid);
+            const float2 k = *(const float2 *)(row + E + 2 * tid);
+            const float2 v = *(const float2 *)(row + 2 * E + 2 * tid);
+            const float q0 = fsub(fmul(q.x, cs.x), fmul(q.y, cs.y)), q1 = fadd(fmul(q.x, cs.y), fmul(q.y, cs.x));
+            const float k0 = fsub(fmul(k.x, cs.x), fmul(k.y, cs.y)), k1 = fadd(fmul(k.x, cs.y), fmul(k.y, cs.x));
+            const uint32_t qq = (uint32_t) f2h(q0) | ((uint32_t) f2h(q1) << 16);
+            const uint32_t kk = (uint32_t) f2h(k0) | ((uint32_t) f2h(k1) << 16);
+            const uint32_t vv = (uint32_t) f2h(v.x) | ((uint32_t) f2h(v.y) << 16);
+            ((uint32_t *) q16s)[tid] = qq; ((uint32_t *) k16s)[tid] = kk; ((uint32_t *) v16s)[tid] = vv;
+            if (g == 0) {
+                *(uint32_t *)(kc + (size_t) pos * E + h * 128 + 2 * tid) = kk;
+                *(uint32_t *)(vc + (size_t) pos * E + h * 128 + 2 * tid) = vv;
+            }
+        }
+    } else {
+        if (tid < 64) ((uint32_t *) q16s)[tid] = *(const uint32_t *)(a.q16 + (size_t) n * E + h * 128 + 2 * tid);
+    }
+    __syncthreads();
+
+    float * scg = a.sc_scratch + ((size_t) ny * a.H + h) * a.n_ctx;
+    // ---- phase 1: scores of the positions this CTA owns
+    {
+        const int sub = tid >> 2, ql = tid & 3;
+        float qf[4][8];
+        #pragma unroll
+        for (int c = 0; c < 4; c++)
+            #pragma unroll
+            for (int e = 0; e < 8; e++) qf[c][e] = h2f(q16s[32 * c + 8 * ql + e]);
+        const int nloc = 8 * ((tcount + 31) >> 5);
+        for (int i = sub; i < nloc; i += 64) {
+            const int t = 32 * (i >> 3) + 8 * g + (i & 7);
+            const bool valid = t < tcount;
+            const uint16_t * krow = (FUSE && t == pos) ? k16s : kc + (size_t) t * E + h * 128;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                uint4 kv[4];
+                #pragma unroll
+                for (int c = 0; c < 4; c++) kv[c] = *(const uint4 *)(krow + 32 * c + 8 * ql);
+                #pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t u[4] = {kv[c].x, kv[c].y, kv[c].z, kv[c].w};
+                    #pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const uint16_t kh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
+                        acc[e] = ffma(h2f(kh), qf[c][e], acc[e]);
+                    }
+                }
+            }
+            float v8[8];
+            #pragma unroll
+            for (int e = 0; e < 8; e++) {                            // (x0 + x2) + (x1 + x3)
+                float x = fadd(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], 2));
+                v8[e] = fadd(x, __shfl_xor_sync(0xffffffffu, x, 1));
+            }
+            const float t0 = fadd(v8[0], v8[4]), t1 = fadd(v8[1], v8[5]), t2 = fadd(v8[2], v8[6]), t3 = fadd(v8[3], v8[7]);
+            const float dot = fadd(fadd(t0, t1), fadd(t2, t3));
+            if (valid && ql == 0) scg[t] = fmul(dot, a.kq_scale);
+        }
+    }
+    __syncthreads();
+    cluster_sync_all();
+
+    // ---- phase 2: softmax over all t < tcount (every CTA, identical results)
+    float mx = -INFINITY;
+    for (int t = tid; t < tcount; t += 256) { const float v = __ldcg(scg + t); sc[t] = v; mx = fmaxf(mx, v); }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) redf[warp] = mx;
+    __syncthreads();
+    mx = redf[0];
+    #pragma unroll
+    for (int i = 1; i < 8; i++) mx = fmaxf(mx, redf[i]);
+    double s = 0.0;
+    for (int t = tid; t < tcount; t += 256) {
+        const float e = h2f(a.texp[f2h(fsub(sc[t], mx))]);
+        sc[t] = e; s += (double) e;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) redd[warp] = s;
+    __syncthreads();
+    double S = 0.0;
+    #pragma unroll
+    for (int i = 0; i < 8; i++) S += redd[i];
+    const float inv = (float)(1.0 / S);
+    for (int t = tid; t < tcount; t += 256) p16[t] = f2h(fmul(sc[t], inv));
+    __syncthreads();
+
+    // ---- phase 3: V.p partial sums of slots 8g..8g+7
+    const int npT = T & ~31, lim = min(npT, tcount);
+    float * partg = a.part_scratch + (((size_t) ny * a.H + h) * 4) * 1024;
+    if (tid < 128) {
+        const int l = tid >> 4, cg = tid & 15;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = 8 * g + l; t < lim; t += 32) {
+            const uint16_t * vrow = (FUSE && t == pos) ? v16s : vc + (size_t) t * E + h * 128;
+            const uint4 vv = *(const uint4 *)(vrow + 8 * cg);
+            const uint32_t u[4] = {vv.x, vv.y, vv.z, vv.w};
+            const float p = h2f(p16[t]);
+            #pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint16_t vh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
+                acc[e] = ffma(h2f(vh), p, acc[e]);
+            }
+        }
+        float4 * dst = (float4 *)(partg + (size_t) g * 1024 + l * 128 + 8 * cg);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    cluster_sync_all();
+
+    // ---- phase 4: CTA g finishes channels [32g, 32g+32)
+    if (tid < 32) {
+        const int c = 32 * g + tid;
+        float vv[8];
+        #pragma unroll
+        for (int l = 0; l < 8; l++) {
+            const float p0 = __ldcg(partg + 0 * 1024 + l * 128 + c), p1 = __ldcg(partg + 1 * 1024 + l * 128 + c);
+            const float p2 = __ldcg(partg + 2 * 1024 + l * 128 + c), p3 = __ldcg(partg + 3 * 1024 + l * 128 + c);
+            vv[l] = fadd(fadd(p0, p2), fadd(p1, p3));
+        }
+        const float t0 = fadd(vv[0], vv[4]), t1 = fadd(vv[1], vv[5]), t2 = fadd(vv[2], vv[6]), t3 = fadd(vv[3], vv[7]);
+        double sumf = (double) fadd(fadd(t0, t1), fadd(t2, t3));
+        for (int t = npT; t < tcount; t++) {
+            const uint16_t vh = (FUSE && t == pos) ? v16s[c] : vc[(size_t) t * E + h * 128 + c];
+            sumf += (double) fmul(h2f(vh), h2f(p16[t]));
+        }
+        const float ov = (float) sumf;
+        a.out[(size_t) n * E + h * 128 + c] = ov;
+        // channels [32g, 32g+32) of head h are Q8_0 block 4h+g of the wo matmul's input: quantise here
+        if (a.aq_out) warp_quant_block(ov, lane, a.aq_out + (size_t) n * a.out_nbq * 32, a.da_out + (size_t) n * a.out_nbq * 4,
+                                       4 * h + g, a.out_dscale);
     }
 }
 

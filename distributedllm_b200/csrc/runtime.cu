@@ -44,12 +44,19 @@ struct b200_slice {
     float * xa = nullptr, * xb = nullptr, * qkv = nullptr, * att = nullptr, * ffin = nullptr, * gate = nullptr;
     float * d_in = nullptr, * d_out = nullptr, * h_in = nullptr, * h_out = nullptr;
     float2 * cs = nullptr; uint16_t * texp = nullptr, * tsilu = nullptr;
+    float * sc_scratch = nullptr, * part_scratch = nullptr;   // k_attn128 exchange buffers
+    int * aq_att = nullptr, * aq_gate = nullptr; float * da_att = nullptr, * da_gate = nullptr;   // pre-quantised activations
+    int nbqE = 0, nbqF = 0;
     std::map<GraphKey, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
     int64_t launches = 0, weight_bytes = 0;
     bool use_ring = true, use_graph = true, use_pdl = false;
     int opt_ns = 0, opt_qs = 0, opt_cta_per_sm = 0;
     std::mutex mu;
+    // per-kernel-class event timing (b200_slice_profile): class 0 qkv, 1 rope, 2 attention, 3 wo, 4 w13, 5 w2, 6 advance
+    bool profiling = false; int cur_class = 0;
+    std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_cls; size_t prof_used = 0;
+    cudaEvent_t mark[2] = {nullptr, nullptr};
     // pipeline (pipeline.cu)
     void * pipe = nullptr;
 };
@@ -65,6 +72,21 @@ template <typename T> static int dev_alloc(b200_slice * s, T ** p, size_t n) {
     s->allocs.push_back(q); *p = (T *) q; return 0;
 }
 
+// ---------------------------------------------------------------- per-launch event brackets
+static void prof_begin(b200_slice * s) {
+    if (!s->profiling) return;
+    if (s->prof_used + 2 > s->prof_ev.size()) {
+        for (int i = 0; i < 2; i++) { cudaEvent_t e; cudaEventCreate(&e); s->prof_ev.push_back(e); }
+    }
+    cudaEventRecord(s->prof_ev[s->prof_used], s->stream);
+}
+static void prof_end(b200_slice * s) {
+    if (!s->profiling) return;
+    cudaEventRecord(s->prof_ev[s->prof_used + 1], s->stream);
+    s->prof_cls.push_back(s->cur_class);
+    s->prof_used += 2;
+}
+
 // ---------------------------------------------------------------- kernel dispatch
 template <int WT, int G, int NC, int PRO, int EPI, bool RING>
 static int launch_gemv_t(b200_slice * s, GemvArgs a) {
@@ -72,11 +94,9 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
     constexpr int TR = kWPC * G;
     auto kern = k_gemv<WT, G, NC, PRO, EPI, RING>;
     static bool attr_set[16] = {false};
-    int QS = s->opt_qs > 0 ? s->opt_qs : 8 / G;
-    if (QS > a.W.nbq) QS = a.W.nbq;
-    const size_t stage = (size_t) QS * TR * CB;
-    const size_t act = (size_t) NC * act_bytes_per_col(a.W.nbq) + 32 * 8 + kWPC * 8 + 64;
-    int NS = RING ? (s->opt_ns > 0 ? s->opt_ns : 4) : 0;
+    const size_t stage = (size_t) kQS * TR * CB;
+    const size_t act = (size_t) NC * act_bytes_per_col(a.W.nbq) + 34 * 8 + kWPC * 8 + (size_t) NC * 128 + 64;
+    int NS = RING ? (s->opt_ns > 0 ? s->opt_ns : 8 / G) : 0;
     while (NS > 2 && NS * stage + act > (size_t) kSmemLimit) NS--;
     if (NS > 16) NS = 16;
     const size_t smem = NS * stage + act;
@@ -85,7 +105,7 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set[s->device & 15] = true;
     }
-    a.QS = QS; a.NS = NS;
+    a.NS = NS;
     int per_sm = s->opt_cta_per_sm > 0 ? s->opt_cta_per_sm : (int)(kSmemLimit / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
@@ -102,7 +122,9 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+    prof_begin(s);
     B200_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    prof_end(s);
     s->launches++;
     return 0;
 }
@@ -127,7 +149,9 @@ static int launch_simple(b200_slice * s, K kern, dim3 grid, dim3 block, size_t s
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+    prof_begin(s);
     B200_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    prof_end(s);
     s->launches++;
     return 0;
 }
@@ -157,6 +181,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         float * nxt = (il == s->L - 1) ? out : ((il & 1) ? s->xb : s->xa);
         uint16_t * kc = s->kc + (size_t) il * s->n_ctx * E, * vc = s->vc + (size_t) il * s->n_ctx * E;
         int rc;
+        s->cur_class = 0;
         if (s->wtype == kWT_F16) {
             GemvF16Args f{}; f.K = E; f.x = cur; f.ldx = E; f.norm_w = Lw.attn_norm; f.N = N; f.tsilu = s->tsilu;
             f.rows = E; f.ldy = 3 * E;
@@ -168,31 +193,70 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu;
             if ((rc = launch_gemv<1, PRO_NORM, EPI_STORE>(s, g))) return rc;
         }
-        RopeArgs ra{s->qkv, E, H, D, N, s->d_npast, s->cs, s->q16, kc, vc};
-        if ((rc = launch_simple(s, k_rope_append, dim3((E / 2 + 255) / 256, N, 1), dim3(256, 1, 1), 0, ra))) return rc;
-        AttnArgs aa{s->q16, kc, vc, s->d_npast, E, H, D, N, s->texp, s->att, 1.0f / sqrtf((float) E / (float) H)};
-        const size_t asm_bytes = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + (size_t) 4 * D * 8 * 4 + 64;
-        if ((rc = launch_simple(s, k_attention, dim3(H, N, 1), dim3(512, 1, 1), asm_bytes, aa))) return rc;
+        if (D == 128) {
+            // head size 128: cluster kernel; for N = 1 RoPE + KV append are fused into its prologue
+            constexpr int kChunk = 32;
+            const size_t asm_bytes = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + 64;
+            Attn128Args aa{};
+            aa.qkv = s->qkv; aa.q16 = s->q16; aa.kc = kc; aa.vc = vc; aa.n_past = s->d_npast; aa.E = E; aa.H = H; aa.N = N;
+            aa.cs = s->cs; aa.texp = s->texp; aa.out = s->att; aa.sc_scratch = s->sc_scratch; aa.part_scratch = s->part_scratch;
+            aa.n_ctx = s->n_ctx; aa.kq_scale = 1.0f / sqrtf((float) E / (float) H);
+            const bool preq = s->wtype != kWT_F16;
+            const float dsc = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
+            if (preq) { aa.aq_out = s->aq_att; aa.da_out = s->da_att; aa.out_nbq = s->nbqE; aa.out_dscale = dsc; }
+            if (N == 1) {
+                s->cur_class = 2;
+                aa.n0 = 0;
+                if ((rc = launch_simple(s, k_attn128<true>, dim3(4 * H, 1, 1), dim3(256, 1, 1), asm_bytes, aa))) return rc;
+            } else {
+                s->cur_class = 1;
+                RopeArgs ra{s->qkv, E, H, D, N, s->d_npast, s->cs, s->q16, kc, vc};
+                if ((rc = launch_simple(s, k_rope_append, dim3((E / 2 + 255) / 256, N, 1), dim3(256, 1, 1), 0, ra))) return rc;
+                s->cur_class = 2;
+                for (int n0 = 0; n0 < N; n0 += kChunk) {
+                    aa.n0 = n0;
+                    const int cnt = N - n0 < kChunk ? N - n0 : kChunk;
+                    if ((rc = launch_simple(s, k_attn128<false>, dim3(4 * H, cnt, 1), dim3(256, 1, 1), asm_bytes, aa))) return rc;
+                }
+            }
+        } else {
+            s->cur_class = 1;
+            RopeArgs ra{s->qkv, E, H, D, N, s->d_npast, s->cs, s->q16, kc, vc};
+            if ((rc = launch_simple(s, k_rope_append, dim3((E / 2 + 255) / 256, N, 1), dim3(256, 1, 1), 0, ra))) return rc;
+            s->cur_class = 2;
+            AttnArgs aa{s->q16, kc, vc, s->d_npast, E, H, D, N, s->texp, s->att, 1.0f / sqrtf((float) E / (float) H)};
+            const size_t asm_bytes = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + (size_t) 4 * D * 8 * 4 + 64;
+            if ((rc = launch_simple(s, k_attention, dim3(H, N, 1), dim3(512, 1, 1), asm_bytes, aa))) return rc;
+        }
         if (s->wtype == kWT_F16) {
             GemvF16Args f{}; f.K = E; f.x = s->att; f.ldx = E; f.N = N; f.tsilu = s->tsilu;
+            s->cur_class = 3;
             f.rows = E; f.W = Lw.f_o; f.resid = cur; f.ldr = E; f.y = s->ffin; f.ldy = E;
             if ((rc = launch_f16<PRO_PLAIN, EPI_RESID>(s, f))) return rc;
+            s->cur_class = 4;
             GemvF16Args g{}; g.K = E; g.x = s->ffin; g.ldx = E; g.norm_w = Lw.ffn_norm; g.N = N; g.tsilu = s->tsilu;
             g.rows = FF; g.W = Lw.f_1; g.W2 = Lw.f_3; g.y = s->gate; g.ldy = FF;
             if ((rc = launch_f16<PRO_NORM, EPI_GATE>(s, g))) return rc;
+            s->cur_class = 5;
             GemvF16Args w{}; w.K = FF; w.x = s->gate; w.ldx = FF; w.N = N; w.tsilu = s->tsilu;
             w.rows = E; w.W = Lw.f_2; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
             if ((rc = launch_f16<PRO_PLAIN, EPI_RESID>(s, w))) return rc;
         } else {
+            const float dsc = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
+            s->cur_class = 3;
             GemvArgs o{}; o.W = Lw.wo; o.x = s->att; o.ldx = E; o.resid = cur; o.ldr = E; o.y = s->ffin; o.ldy = E;
-            o.N = N; o.out_rows = E; o.tsilu = s->tsilu;
-            if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID>(s, o))) return rc;
+            o.N = N; o.out_rows = E; o.tsilu = s->tsilu; o.aq_in = s->aq_att; o.da_in = s->da_att;
+            if (D == 128) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, o))) return rc; }
+            else          { if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID>(s, o))) return rc; }
+            s->cur_class = 4;
             GemvArgs g{}; g.W = Lw.w13; g.x = s->ffin; g.ldx = E; g.norm_w = Lw.ffn_norm; g.y = s->gate; g.ldy = FF;
             g.N = N; g.out_rows = FF; g.tsilu = s->tsilu;
-            if ((rc = launch_gemv<2, PRO_NORM, EPI_GATE>(s, g))) return rc;
-            GemvArgs w{}; w.W = Lw.w2; w.x = s->gate; w.ldx = FF; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
-            w.N = N; w.out_rows = E; w.tsilu = s->tsilu;
-            if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID>(s, w))) return rc;
+            g.aq_out = s->aq_gate; g.da_out = s->da_gate; g.out_nbq = s->nbqF; g.out_dscale = dsc;
+            if ((rc = launch_gemv<2, PRO_NORM, EPI_GATEQ>(s, g))) return rc;
+            s->cur_class = 5;
+            GemvArgs w{}; w.W = Lw.w2; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
+            w.N = N; w.out_rows = E; w.tsilu = s->tsilu; w.aq_in = s->aq_gate; w.da_in = s->da_gate;
+            if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, w))) return rc;
         }
         cur = nxt;
     }
@@ -203,7 +267,10 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+        s->cur_class = 6;
+        prof_begin(s);
         B200_CUDA(cudaLaunchKernelEx(&cfg, k_advance, s->d_npast, N));
+        prof_end(s);
         s->launches++;
     }
     return 0;
@@ -213,7 +280,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
 static int run_decode_graph(b200_slice * s, const float * in, float * out, bool host) {
     GraphKey key{in, out, host};
     auto it = s->graphs.find(key);
-    const int per_step = 6 * s->L + (s->wtype == kWT_F16 ? 2 * s->L : 0) + 1;
+    const int per_step = (s->D == 128 ? 5 : 6) * s->L + (s->wtype == kWT_F16 ? 2 * s->L : 0) + 1;
     if (it == s->graphs.end()) {
         const int64_t before = s->launches;
         cudaGraph_t g = nullptr;
@@ -250,7 +317,7 @@ static int forward_locked(b200_slice * s, const float * in, int N, float * out, 
     B200_CUDA(cudaEventRecord(s->ev0, s->stream));
     int rc;
     if (host) {
-        if (N == 1 && s->use_graph) {
+        if (N == 1 && s->use_graph && !s->profiling) {
             memcpy(s->h_in, in, (size_t) s->E * 4);
             if ((rc = run_decode_graph(s, nullptr, nullptr, true))) return rc;
             B200_CUDA(cudaEventRecord(s->ev1, s->stream));
@@ -264,7 +331,7 @@ static int forward_locked(b200_slice * s, const float * in, int N, float * out, 
             B200_CUDA(cudaStreamSynchronize(s->stream));
         }
     } else {
-        if (N == 1 && s->use_graph) { if ((rc = run_decode_graph(s, in, out, false))) return rc; }
+        if (N == 1 && s->use_graph && !s->profiling) { if ((rc = run_decode_graph(s, in, out, false))) return rc; }
         else if ((rc = enqueue_layers(s, in, N, out))) return rc;
         B200_CUDA(cudaEventRecord(s->ev1, s->stream));
     }
@@ -285,7 +352,7 @@ static int pack_matrix(b200_slice * s, const GgjtFile & f, const GgjtTensor * co
                        uint8_t * scratch, PackedW * out) {
     const int wt = (int) src[0]->type;
     const int K = (int) src[0]->ne[0], rows_per = (int) src[0]->ne[1];
-    const int nb = K / 32, nbq = (nb + 3) / 4, TR = kWPC * G;
+    const int nb = K / 32, nbq = ((nb + 3) / 4 + kQS - 1) / kQS * kQS, TR = kWPC * G;
     const int total_groups = (rows_per + 7) / 8 * nsrc;
     const int n_tiles = (total_groups + TR - 1) / TR;
     const int cb = chunk_bytes(wt);
@@ -418,8 +485,17 @@ static int load_locked(b200_slice * s, const char * path) {
         (rc = dev_alloc(s, &s->q16, nE)) || (rc = dev_alloc(s, &s->xa, nE)) || (rc = dev_alloc(s, &s->xb, nE)) ||
         (rc = dev_alloc(s, &s->qkv, 3 * nE)) || (rc = dev_alloc(s, &s->att, nE)) || (rc = dev_alloc(s, &s->ffin, nE)) ||
         (rc = dev_alloc(s, &s->gate, (size_t) s->n_ctx * FF)) || (rc = dev_alloc(s, &s->d_in, nE)) ||
-        (rc = dev_alloc(s, &s->d_out, nE)) || (rc = dev_alloc(s, &s->d_npast, 1)))
+        (rc = dev_alloc(s, &s->d_out, nE)) || (rc = dev_alloc(s, &s->d_npast, 1)) ||
+        (rc = dev_alloc(s, &s->sc_scratch, (size_t) 32 * s->H * s->n_ctx)) || (rc = dev_alloc(s, &s->part_scratch, (size_t) 32 * s->H * 4096)))
         return rc;
+    if (s->wtype != kWT_F16) {
+        s->nbqE = s->layers[0].wo.nbq; s->nbqF = s->layers[0].w2.nbq;
+        const size_t nq = (size_t) s->n_ctx;
+        if ((rc = dev_alloc(s, &s->aq_att, nq * s->nbqE * 32)) || (rc = dev_alloc(s, &s->da_att, nq * s->nbqE * 4)) ||
+            (rc = dev_alloc(s, &s->aq_gate, nq * s->nbqF * 32)) || (rc = dev_alloc(s, &s->da_gate, nq * s->nbqF * 4))) return rc;
+        B200_CUDA(cudaMemset(s->aq_att, 0, nq * s->nbqE * 128));  B200_CUDA(cudaMemset(s->da_att, 0, nq * s->nbqE * 16));
+        B200_CUDA(cudaMemset(s->aq_gate, 0, nq * s->nbqF * 128)); B200_CUDA(cudaMemset(s->da_gate, 0, nq * s->nbqF * 16));
+    }
     B200_CUDA(cudaMemset(s->kc, 0, (size_t) s->L * nE * 2));
     B200_CUDA(cudaMemset(s->vc, 0, (size_t) s->L * nE * 2));
     B200_CUDA(cudaMemset(s->d_npast, 0, 4));
@@ -427,6 +503,8 @@ static int load_locked(b200_slice * s, const char * path) {
     B200_CUDA(cudaMallocHost((void **) &s->h_out, (size_t) E * 4));
     if ((rc = build_tables(s))) return rc;
     B200_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    B200_CUDA(cudaFuncSetAttribute(k_attn128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(k_attn128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B200_CUDA(cudaEventCreate(&s->ev0));
     B200_CUDA(cudaEventCreate(&s->ev1));
     B200_CUDA(cudaDeviceSynchronize());
@@ -442,6 +520,8 @@ static void destroy(b200_slice * s) {
     if (s->h_out) cudaFreeHost(s->h_out);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) if (s->mark[i]) cudaEventDestroy(s->mark[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -470,7 +550,7 @@ int b200_slice_load(const char * path, int device, int n_ctx, b200_slice_t ** ou
     s->n_ctx = n_ctx > 0 ? n_ctx : 512;               // vendor examples/common.h:28
     s->use_ring  = env_int("B200_RING", 1) != 0;
     s->use_graph = env_int("B200_GRAPH", 1) != 0;
-    s->use_pdl   = env_int("B200_PDL", 0) != 0;
+    s->use_pdl   = env_int("B200_PDL", 1) != 0;
     s->opt_ns = env_int("B200_NS", 0); s->opt_qs = env_int("B200_QS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0);
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
@@ -549,6 +629,46 @@ float b200_slice_last_ms(b200_slice_t * s) {
 int64_t b200_slice_launch_count(b200_slice_t * s) { return s ? s->launches : 0; }
 float * b200_slice_dev_in(b200_slice_t * s)  { return s ? s->d_in : nullptr; }
 float * b200_slice_dev_out(b200_slice_t * s) { return s ? s->d_out : nullptr; }
+
+int b200_slice_mark(b200_slice_t * s, int which) {
+    if (!s || which < 0 || which > 1) return fail(B200_EINVAL, "bad argument");
+    B200_CUDA(cudaSetDevice(s->device));
+    if (!s->mark[which]) B200_CUDA(cudaEventCreate(&s->mark[which]));
+    B200_CUDA(cudaEventRecord(s->mark[which], s->stream));
+    return 0;
+}
+
+float b200_slice_mark_elapsed_ms(b200_slice_t * s) {
+    if (!s || !s->mark[0] || !s->mark[1]) return -1.f;
+    float ms = -1.f;
+    cudaSetDevice(s->device);
+    if (cudaEventSynchronize(s->mark[1]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, s->mark[0], s->mark[1]) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+int b200_slice_profile(b200_slice_t * s, int enable) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->profiling = enable != 0; s->prof_used = 0; s->prof_cls.clear();
+    return 0;
+}
+
+int b200_slice_profile_read(b200_slice_t * s, float * ms_by_class, int * launches_by_class, int n_class) {
+    if (!s || !ms_by_class || !launches_by_class) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < n_class; i++) { ms_by_class[i] = 0.f; launches_by_class[i] = 0; }
+    for (size_t i = 0; i < s->prof_cls.size(); i++) {
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[2 * i], s->prof_ev[2 * i + 1]));
+        const int c = s->prof_cls[i];
+        if (c < n_class) { ms_by_class[c] += ms; launches_by_class[c]++; }
+    }
+    s->prof_used = 0; s->prof_cls.clear();
+    return 0;
+}
 
 /* Test hook: copy `count` 32-bit words of an internal activation buffer to the host after a
  * forward (0 qkv, 1 att, 2 ffin, 3 gate, 4 xa, 5 xb, 6 q16, 7 k-cache, 8 v-cache). */

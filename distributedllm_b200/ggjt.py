@@ -321,6 +321,7 @@ class ModelShape:
 SHAPES = {
     "tiny":   ModelShape(512, 256, 32, 4, 4),        # d_head 64, n_ff 704
     "tiny3b": ModelShape(512, 800, 32, 8, 3),        # d_head 100 (OpenLLaMA-3B-like head), n_ff 2144 = 67 blocks
+    "tiny128": ModelShape(512, 512, 32, 4, 3),       # d_head 128 (the 7B/13B head size), n_ff 1376 = 43 blocks
     "3b":     ModelShape(32000, 3200, 216, 32, 26),  # OpenLLaMA-3B: n_ff 8640
     "7b":     ModelShape(32000, 4096, 256, 32, 32),
     "13b":    ModelShape(32000, 5120, 256, 40, 40),
@@ -404,11 +405,28 @@ def write_synth_full(path: str, shape: ModelShape, wtype: int = T_F32, seed: int
     write_file(path, hp, vocab, gen())
 
 
+_POOL_BLOCKS = 1 << 21          # 2 Mi blocks = 36 MiB per pool
+
+
+def _fast_q4_pool(seed: int, k: int) -> np.ndarray:
+    """A pool of random Q4_0 blocks: uniform nibbles, fp16 scale = +-mag*(1 + j/512), j in [-128,128),
+    mag = 1/(4.6*sqrt(fan_in)) so that weights have std ~ 1/sqrt(fan_in)."""
+    rng = np.random.default_rng([seed, k, 77])
+    blocks = rng.integers(0, 256, size=(_POOL_BLOCKS, 18), dtype=np.uint8)
+    mag = 1.0 / (4.6 * np.sqrt(k))
+    lut = (mag * (1.0 + (np.arange(256, dtype=np.float32) - 128.0) / 512.0)).astype(np.float16).view(np.uint16)
+    d = lut[blocks[:, 1]] | ((blocks[:, 0] & 1).astype(np.uint16) << 15)
+    blocks[:, 0] = (d & 0xFF).astype(np.uint8)
+    blocks[:, 1] = (d >> 8).astype(np.uint8)
+    return blocks
+
+
 def write_fast_q4_slice(path: str, shape: ModelShape, layer_from: int, layer_to: int, seed: int = 0) -> int:
-    """Large-model generator for benchmarks: writes Q4_0 blocks directly (uniform random nibbles,
-    per-block fp16 scale +-1/(4.6*sqrt(fan_in)) so weights have std ~ 1/sqrt(fan_in)) instead of
-    quantising 6.5e9 Gaussians.  The file is the ground truth for both the B200 path and the CPU
-    reference, so the distribution only has to keep activations finite.  Returns bytes written."""
+    """Large-model generator for benchmarks.  Quantising 6.5e9 Gaussians takes minutes, so Q4_0
+    blocks are written directly: each matrix is a window (at a per-tensor pseudo-random block
+    offset, wrapping) into a 36 MiB pool of random blocks built once per fan-in.  The file is the
+    ground truth for both the B200 path and the CPU reference, so the distribution only has to keep
+    activations finite; any layer range of the same (shape, seed) is reproducible.  Returns bytes written."""
     vocab = default_vocab(shape.n_vocab)
     hp = HParams(shape.n_vocab, shape.n_embd, shape.n_mult, shape.n_head, layer_to - layer_from + 1,
                  shape.n_embd // shape.n_head, FTYPE_Q4_0, layer_from)
@@ -416,23 +434,30 @@ def write_fast_q4_slice(path: str, shape: ModelShape, layer_from: int, layer_to:
     dims = {"attention.wq.weight": (e, e), "attention.wk.weight": (e, e), "attention.wv.weight": (e, e),
             "attention.wo.weight": (e, e), "feed_forward.w1.weight": (ff, e), "feed_forward.w2.weight": (e, ff),
             "feed_forward.w3.weight": (ff, e)}
+    pools = {k: memoryview(_fast_q4_pool(seed, k)).cast("B") for k in sorted({e, ff})}
+    pool_bytes = _POOL_BLOCKS * 18
     with open(path, "wb") as f:
         _write_header(f, hp, vocab)
         for layer in range(layer_from, layer_to + 1):
-            rng = np.random.default_rng([seed, layer, 77])
             pre = "layers.%d." % layer
+            rng = np.random.default_rng([seed, layer, 78])
             for nm in LAYER_TENSORS:
                 if nm.endswith("norm.weight"):
                     w = (1.0 + 0.1 * rng.standard_normal(e)).astype(np.float32)
                     _write_tensor(f, pre + nm, T_F32, (e,), w.tobytes())
                     continue
                 rows, k = dims[nm]
-                nblk = rows * k // QK
-                blocks = rng.integers(0, 256, size=(nblk, 18), dtype=np.uint8)
-                mag = np.float16(1.0 / (4.6 * np.sqrt(k)))
-                sign = (blocks[:, 0] & 1).astype(np.float16) * np.float16(2) - np.float16(1)
-                jit = (1.0 + (blocks[:, 1].astype(np.float32) - 128.0) / 512.0).astype(np.float16)
-                d = (sign * mag * jit).astype(np.float16)
-                blocks[:, 0:2] = d.view(np.uint8).reshape(nblk, 2)
-                _write_tensor(f, pre + nm, T_Q4_0, (k, rows), blocks.tobytes())
+                nbytes = rows * k // QK * 18
+                start = int(rng.integers(0, _POOL_BLOCKS)) * 18
+                name = (pre + nm).encode("utf-8")
+                f.write(struct.pack("<III", 2, len(name), T_Q4_0))
+                f.write(struct.pack("<2I", k, rows))
+                f.write(name)
+                f.write(b"\0" * ((-f.tell()) & 31))
+                left, pos = nbytes, start
+                while left:
+                    n = min(left, pool_bytes - pos)
+                    f.write(pools[k][pos:pos + n])
+                    left -= n
+                    pos = 0
         return f.tell()

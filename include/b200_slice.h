@@ -82,6 +82,18 @@ int b200_slice_sync(b200_slice_t * s);
  * (CUDA events on the slice's stream); -1 if none. */
 float b200_slice_last_ms(b200_slice_t * s);
 
+/* Record CUDA event `which` (0 = start, 1 = stop) on the slice's stream, and read the time between
+ * them: how bench.py times K steps on the stream the kernels are launched on. */
+int b200_slice_mark(b200_slice_t * s, int which);
+float b200_slice_mark_elapsed_ms(b200_slice_t * s);
+
+/* Per-kernel event timing.  While enabled, forwards run un-graphed with one CUDA-event pair around
+ * every launch; _read() returns the summed device time and launch count per kernel class
+ * (0 qkv matmul, 1 rope+append, 2 attention, 3 wo matmul, 4 w1/w3 matmul, 5 w2 matmul, 6 advance)
+ * since the last read. */
+int b200_slice_profile(b200_slice_t * s, int enable);
+int b200_slice_profile_read(b200_slice_t * s, float * ms_by_class, int * launches_by_class, int n_class);
+
 /* Number of kernel launches (graph nodes included) issued by this handle so far. */
 int64_t b200_slice_launch_count(b200_slice_t * s);
 

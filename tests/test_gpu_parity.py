@@ -36,8 +36,9 @@ def _run_pair(path, calls, shape, n_ctx=512, seed=1):
     return bad, tot
 
 
-@pytest.mark.parametrize("shape,wtype", [("tiny", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q4_0), ("tiny", ggjt.T_Q8_0),
-                                         ("tiny", ggjt.T_F16), ("tiny3b", ggjt.T_F16)])
+@pytest.mark.parametrize("shape,wtype", [("tiny", ggjt.T_Q4_0), ("tiny128", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q4_0),
+                                         ("tiny", ggjt.T_Q8_0), ("tiny128", ggjt.T_Q8_0), ("tiny", ggjt.T_F16),
+                                         ("tiny3b", ggjt.T_F16), ("tiny128", ggjt.T_F16)])
 def test_bit_exact_prefill_then_decode(tmp_models, shape, wtype):
     sh = ggjt.SHAPES[shape]
     path = tmp_models(shape, wtype, 1, 2)
@@ -54,10 +55,22 @@ def test_ring_and_simple_kernels_agree(tmp_models, monkeypatch):
         assert bad == 0, "ring=%s: %d of %d floats differ" % (ring, bad, tot)
 
 
-def test_decode_only_long(tmp_models):
-    sh = ggjt.SHAPES["tiny"]
-    path = tmp_models("tiny", ggjt.T_Q4_0, 0, 3)
+@pytest.mark.parametrize("shape", ["tiny", "tiny128"])
+def test_decode_only_long(tmp_models, shape):
+    sh = ggjt.SHAPES[shape]
+    path = tmp_models(shape, ggjt.T_Q4_0, 0, 2)
     bad, tot = _run_pair(path, [1] * 70, sh)
+    assert bad == 0
+
+
+@pytest.mark.parametrize("pdl,graph", [("0", "1"), ("1", "0"), ("0", "0")])
+def test_launch_modes_agree(tmp_models, monkeypatch, pdl, graph):
+    """Programmatic dependent launch and CUDA-graph replay are scheduling choices only."""
+    monkeypatch.setenv("B200_PDL", pdl)
+    monkeypatch.setenv("B200_GRAPH", graph)
+    sh = ggjt.SHAPES["tiny128"]
+    path = tmp_models("tiny128", ggjt.T_Q4_0, 0, 2)
+    bad, tot = _run_pair(path, [37, 1, 1, 1, 30, 1, 1], sh)
     assert bad == 0
 
 
