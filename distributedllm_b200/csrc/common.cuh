@@ -66,6 +66,10 @@ __device__ __forceinline__ void bulk_g2s(void * dst_smem, const void * src_gmem,
 __device__ __forceinline__ void grid_dep_wait()   { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// debug timeline: 8 timestamps per CTA (blockIdx.x + gridDim.x * blockIdx.y)
+#define B200_TRACE(ptr, slot) do { if (ptr) (ptr)[((size_t) blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = b200::gtime(); } while (0)
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }

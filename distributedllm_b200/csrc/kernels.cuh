@@ -131,7 +131,7 @@ __global__ void k_repack(RepackArgs a) {
 //   * epilogue (fused): store | + residual | SiLU(w1 x) * (w3 x)
 // =============================================================================================
 enum { PRO_PLAIN = 0, PRO_NORM = 1, PRO_PREQ = 2 };
-enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GATE = 2, EPI_GATEQ = 3 };
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GATE = 2, EPI_GATEQ = 3, EPI_RESID_NQ = 4 };
 
 struct GemvArgs {
     PackedW W;
@@ -140,11 +140,16 @@ struct GemvArgs {
     const int * aq_in; const float * da_in;   // PRO_PREQ: pre-quantised input, [N][nbq*32] words + [N][nbq*4] scales
     const float * resid;  int ldr;       // EPI_RESID
     float * y;            int ldy;       // output [N][ldy]
-    int * aq_out; float * da_out; int out_nbq; float out_dscale;   // EPI_GATEQ: quantised output for the next matmul
+    int * aq_out; float * da_out; int out_nbq; float out_dscale;   // EPI_GATEQ / EPI_RESID_NQ: quantised output for the next matmul
+    const float * nq_norm_w; int * nq_counter;   // EPI_RESID_NQ: next RMSNorm weight [out_rows]; one ticket counter per column group
     int N;                               // columns (tokens)
     int out_rows;                        // valid output rows (E, 3E, or FF for the gate)
     const uint16_t * tsilu;              // EPI_GATE*: fp16 SiLU table (65536 entries)
     int NS;                              // ring stages
+    unsigned long long * trace;          // debug timeline (B200_TRACE), or null
+    int pdl_early;                       // trigger dependents at kernel start instead of after the last weight copy
+    int swp;                             // software-pipelined decode loop
+    int dbg_nomath;                      // debug: consume ring stages without computing (streaming-rate probe)
 };
 
 __host__ __device__ inline size_t act_bytes_per_col(int nbq) { return (size_t) nbq * (128 + 16); }
@@ -209,6 +214,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
     const int n_stage = nbq / kQS;
 
     if (tid == 0) {
+        B200_TRACE(a.trace, 0);
         if (RING) for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWPC); }
         mbar_init(actbar, 1);
         mbar_fence_init();
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
     if (RING && warp == kWPC) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
-            grid_dep_launch();
+            if (a.pdl_early) grid_dep_launch();
             int slot = 0, use = 0;
             for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
                 const uint8_t * src = a.W.data + (long long) tile * a.W.tile_bytes;
@@ -229,6 +235,10 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                     if (++slot == NS) { slot = 0; use++; }
                 }
             }
+            // This CTA has requested its last weight byte: let the NEXT kernel's CTAs become resident and
+            // start THEIR weight stream now, so HBM never idles across the kernel boundary (depth-1 hand-off).
+            if (!a.pdl_early) grid_dep_launch();
+            B200_TRACE(a.trace, 4);
         }
         return;
     }
@@ -236,6 +246,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
     // ---------------------------------------------------------------------- consumer warps
     if (!RING && tid == 0) grid_dep_launch();
     grid_dep_wait();                                   // the input comes from the previous kernel
+    if (tid == 0) B200_TRACE(a.trace, 1);
 
     const int ncols = min(NC, a.N - col0);
     if (PRO == PRO_PREQ) {
@@ -325,6 +336,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
         }
     }
     named_bar_sync(1, kConsumers);
+    if (tid == 0) B200_TRACE(a.trace, 2);
 
     const int r = lane >> 2, w = lane & 3;
     int slot = 0, phase = 0;
@@ -336,6 +348,82 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             for (int n = 0; n < NC; n++) { acc[g][n][0] = 0.f; acc[g][n][1] = 0.f; }
         const uint8_t * gsrc = a.W.data + (long long) tile * a.W.tile_bytes;
 
+        if (NC == 1 && !a.dbg_nomath && a.swp) {
+            // ---- decode path: software-pipelined over units of PQ quads.  Unit u+1's shared-memory loads
+            // (weights, scales, activation words) are issued into a second register set BEFORE unit u is
+            // computed, so the LDS latency hides behind ~100+ instructions of math; a ring stage is handed back to the
+            // producer as soon as its last unit sits in registers, not when it has been computed.
+            constexpr int PQ = (G == 1) ? 4 : 2;           // quads per unit
+            constexpr int UPS = kQS / PQ;                   // units per stage
+            const int n_unit = n_stage * UPS;
+            uint4 Wb[2][PQ][G], W2b[2][PQ][G]; uint2 Sb[2][PQ][G]; int4 A0[2][PQ], A1[2][PQ]; float4 DA[2][PQ];
+            const int * a_base = a_s + w * 8;
+            auto load_unit = [&](int buf, int u) {
+                const int st = u / UPS, uu = u - st * UPS;
+                const uint8_t * base;
+                if (RING) {
+                    if (uu == 0) mbar_wait(&full[slot], phase);
+                    base = ring + (size_t) slot * stage_bytes;
+                } else base = gsrc + (size_t) st * stage_bytes;
+                base += (size_t)(warp * G) * CB + (size_t)(uu * PQ * TR) * CB;
+                #pragma unroll
+                for (int qi = 0; qi < PQ; qi++) {
+                    #pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const uint8_t * ch = base + (size_t)(qi * TR + g) * CB;
+                        Wb[buf][qi][g] = *(const uint4 *)(ch + lane * 16);
+                        if (WT == kWT_Q8_0) { W2b[buf][qi][g] = *(const uint4 *)(ch + 512 + lane * 16); Sb[buf][qi][g] = *(const uint2 *)(ch + 1024 + r * 8); }
+                        else Sb[buf][qi][g] = *(const uint2 *)(ch + 512 + r * 8);
+                    }
+                    const int Q = u * PQ + qi;
+                    const int4 * ap = (const int4 *)(a_base + Q * 32);
+                    A0[buf][qi] = ap[0]; A1[buf][qi] = ap[1];
+                    DA[buf][qi] = *(const float4 *)(da_s + Q * 4);
+                }
+                if (RING && uu == UPS - 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[slot]);
+                    if (++slot == NS) { slot = 0; phase ^= 1; }
+                }
+            };
+            auto compute_unit = [&](int buf) {
+                #pragma unroll
+                for (int qi = 0; qi < PQ; qi++) {
+                    const int4 a01 = A0[buf][qi], a23 = A1[buf][qi];
+                    const float4 dav = DA[buf][qi];
+                    const int alo[4] = {a01.x, a01.z, a23.x, a23.z};
+                    const int ahi[4] = {a01.y, a01.w, a23.y, a23.w};
+                    const float da[4] = {dav.x, dav.y, dav.z, dav.w};
+                    #pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const uint32_t ww[4] = {Wb[buf][qi][g].x, Wb[buf][qi][g].y, Wb[buf][qi][g].z, Wb[buf][qi][g].w};
+                        const uint32_t ww2[4] = {W2b[buf][qi][g].x, W2b[buf][qi][g].y, W2b[buf][qi][g].z, W2b[buf][qi][g].w};
+                        const uint32_t sw[2] = {Sb[buf][qi][g].x, Sb[buf][qi][g].y};
+                        #pragma unroll
+                        for (int bq = 0; bq < 4; bq++) {
+                            const uint16_t dh = (uint16_t)(sw[bq >> 1] >> (16 * (bq & 1)));
+                            const float D = fmul(h2f(dh), da[bq]);
+                            int lo, hi;
+                            if (WT == kWT_Q4_0) { lo = (int)((ww[bq] << 4) & 0xF0F0F0F0u); hi = (int)(ww[bq] & 0xF0F0F0F0u); }
+                            else                { lo = (int) ww[bq]; hi = (int) ww2[bq]; }
+                            const float f0 = fadd(__int_as_float(__dp4a(lo, alo[bq], kMagicI)), -kMagic);
+                            const float f1 = fadd(__int_as_float(__dp4a(hi, ahi[bq], kMagicI)), -kMagic);
+                            acc[g][0][0] = ffma(D, f0, acc[g][0][0]);
+                            acc[g][0][1] = ffma(D, f1, acc[g][0][1]);
+                        }
+                    }
+                }
+            };
+            load_unit(0, 0);
+            for (int u = 0; u < n_unit; u += 2) {
+                if (u + 1 < n_unit) load_unit(1, u + 1);
+                compute_unit(0);
+                if (u + 1 < n_unit) {
+                    if (u + 2 < n_unit) load_unit(0, u + 2);
+                    compute_unit(1);
+                }
+            }
+        } else
         for (int s = 0; s < n_stage; s++) {
             const uint8_t * base;
             if (RING) {
@@ -345,6 +433,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 base = gsrc + (size_t) s * stage_bytes;
             }
             base += (size_t)(warp * G) * CB;
+            if (!a.dbg_nomath)
             #pragma unroll
             for (int qi = 0; qi < kQS; qi++) {
                 const int Q = s * kQS + qi;
@@ -429,7 +518,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                     for (int n = 0; n < NC; n++) {
                         if (n < ncols) {
                             float v = res[g][n];
-                            if (EPI == EPI_RESID) v = fadd(v, a.resid[(size_t)(col0 + n) * a.ldr + row]);
+                            if (EPI == EPI_RESID || EPI == EPI_RESID_NQ) v = fadd(v, a.resid[(size_t)(col0 + n) * a.ldr + row]);
                             a.y[(size_t)(col0 + n) * a.ldy + row] = v;
                         }
                     }
@@ -437,6 +526,109 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             }
         }
     }
+    if (EPI == EPI_RESID_NQ) {
+        // The output vector feeds an RMSNorm + weight matmul next.  The LAST CTA of this column group to finish
+        // (ticket counter) normalises and Q8_0-quantises the whole row(s) once, so the next kernel starts from a
+        // 4.6 KB bulk copy instead of every one of its CTAs re-reading and re-normalising x behind the weight stream.
+        __shared__ int is_last;
+        __threadfence();
+        named_bar_sync(1, kConsumers);
+        if (tid == 0) {
+            const int ticket = atomicAdd(a.nq_counter + blockIdx.y, 1);
+            is_last = ticket == (int) gridDim.x - 1;
+            if (is_last) a.nq_counter[blockIdx.y] = 0;
+        }
+        named_bar_sync(1, kConsumers);
+        if (is_last) {
+            __threadfence();
+            const int Ko = a.out_rows, nbo = Ko / 32;
+            for (int n = 0; n < ncols; n++) {
+                const float * yrow = a.y + (size_t)(col0 + n) * a.ldy;
+                int * aq = a.aq_out + (size_t)(col0 + n) * a.out_nbq * 32;
+                float * dq = a.da_out + (size_t)(col0 + n) * a.out_nbq * 4;
+                if (nbo <= kConsumers) {
+                    // one L2 round trip: the row and the norm weights in flight together, row kept in registers
+                    float v[32], wn[32];
+                    const bool own = tid < nbo;
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 t = own ? __ldcg((const float4 *)(yrow + tid * 32 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 u = own ? *(const float4 *)(a.nq_norm_w + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
+                        wn[j*4] = u.x; wn[j*4+1] = u.y; wn[j*4+2] = u.z; wn[j*4+3] = u.w;
+                    }
+                    double s = 0.0;
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++) s += (double) fmul(v[j], v[j]);
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) red[warp] = s;
+                    named_bar_sync(1, kConsumers);
+                    const double tot = (red[0] + red[1]) + (red[2] + red[3]);
+                    named_bar_sync(1, kConsumers);
+                    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) Ko), 1e-6f)));
+                    if (own) {
+                        #pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = fmul(fmul(v[j], scale), wn[j]);
+                        float amax = 0.f;
+                        #pragma unroll
+                        for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
+                        const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
+                        const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
+                        dq[tid] = fmul(d, a.out_dscale);
+                        int * dst = aq + (tid >> 2) * 32 + (tid & 3) * 2;
+                        #pragma unroll
+                        for (int w8 = 0; w8 < 8; w8++) {
+                            uint32_t pk = 0;
+                            #pragma unroll
+                            for (int j = 0; j < 4; j++) pk |= ((uint32_t)(__float2int_rn(fmul(v[w8*4 + j], id)) & 0xFF)) << (8 * j);
+                            dst[(w8 & 3) * 8 + (w8 >> 2)] = (int) pk;
+                        }
+                    }
+                    continue;
+                }
+                double s = 0.0;
+                for (int b = tid; b < nbo; b += kConsumers) {
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 v = __ldcg((const float4 *)(yrow + b * 32 + j * 4));
+                        s += (double) fmul(v.x, v.x); s += (double) fmul(v.y, v.y);
+                        s += (double) fmul(v.z, v.z); s += (double) fmul(v.w, v.w);
+                    }
+                }
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) red[warp] = s;
+                named_bar_sync(1, kConsumers);
+                const double tot = (red[0] + red[1]) + (red[2] + red[3]);
+                named_bar_sync(1, kConsumers);
+                const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) Ko), 1e-6f)));
+                for (int b = tid; b < nbo; b += kConsumers) {
+                    float v[32];
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 t = __ldcg((const float4 *)(yrow + b * 32 + j * 4));
+                        const float4 wv = *(const float4 *)(a.nq_norm_w + b * 32 + j * 4);
+                        v[j*4] = fmul(fmul(t.x, scale), wv.x); v[j*4+1] = fmul(fmul(t.y, scale), wv.y);
+                        v[j*4+2] = fmul(fmul(t.z, scale), wv.z); v[j*4+3] = fmul(fmul(t.w, scale), wv.w);
+                    }
+                    float amax = 0.f;
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
+                    const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
+                    const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
+                    dq[b] = fmul(d, a.out_dscale);
+                    int * dst = aq + (b >> 2) * 32 + (b & 3) * 2;
+                    #pragma unroll
+                    for (int w8 = 0; w8 < 8; w8++) {
+                        uint32_t pk = 0;
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) pk |= ((uint32_t)(__float2int_rn(fmul(v[w8*4 + j], id)) & 0xFF)) << (8 * j);
+                        dst[(w8 & 3) * 8 + (w8 >> 2)] = (int) pk;
+                    }
+                }
+            }
+        }
+    }
+    if (tid == 0) B200_TRACE(a.trace, 3);
 }
 
 // =============================================================================================
@@ -703,6 +895,7 @@ struct Attn128Args {
     float * sc_scratch;           // [chunk][H][n_ctx]
     float * part_scratch;         // [chunk][H][4][8][128]
     int n_ctx; float kq_scale;
+    unsigned long long * trace;
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -715,8 +908,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(16) uint16_t q16s[128], k16s[128], v16s[128];
     __shared__ double redd[8]; __shared__ float redf[8];
-    if (threadIdx.x == 0) grid_dep_launch();
+    if (threadIdx.x == 0) { B200_TRACE(a.trace, 0); grid_dep_launch(); }
     grid_dep_wait();
+    if (threadIdx.x == 0) B200_TRACE(a.trace, 1);
     const int h = blockIdx.x >> 2, g = blockIdx.x & 3, ny = blockIdx.y, n = a.n0 + ny, E = a.E;
     const int n_past = *a.n_past, T = n_past + a.N, tcount = n_past + n + 1, pos = n_past + n;
     float * sc = (float *) smem;                                   // [T]
@@ -861,6 +1055,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
         if (a.aq_out) warp_quant_block(ov, lane, a.aq_out + (size_t) n * a.out_nbq * 32, a.da_out + (size_t) n * a.out_nbq * 4,
                                        4 * h + g, a.out_dscale);
     }
+    if (threadIdx.x == 0) B200_TRACE(a.trace, 3);
 }
 
 // position counter kept on the device so a captured graph can be replayed for every token

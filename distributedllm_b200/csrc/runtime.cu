@@ -8,6 +8,7 @@
 #include "ggjt_file.hpp"
 
 #include <cmath>
+#include <dlfcn.h>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -47,18 +48,21 @@ struct b200_slice {
     float * sc_scratch = nullptr, * part_scratch = nullptr;   // k_attn128 exchange buffers
     int * aq_att = nullptr, * aq_gate = nullptr; float * da_att = nullptr, * da_gate = nullptr;   // pre-quantised activations
     int nbqE = 0, nbqF = 0;
+    int * aq_x = nullptr; float * da_x = nullptr; int * nq_counter = nullptr;   // normalised+quantised layer input (last-CTA epilogue)
     std::map<GraphKey, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
     int64_t launches = 0, weight_bytes = 0;
-    bool use_ring = true, use_graph = true, use_pdl = false;
+    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true;
     int opt_ns = 0, opt_qs = 0, opt_cta_per_sm = 0;
     std::mutex mu;
     // per-kernel-class event timing (b200_slice_profile): class 0 qkv, 1 rope, 2 attention, 3 wo, 4 w13, 5 w2, 6 advance
     bool profiling = false; int cur_class = 0;
     std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_cls; size_t prof_used = 0;
     cudaEvent_t mark[2] = {nullptr, nullptr};
-    // pipeline (pipeline.cu)
-    void * pipe = nullptr;
+    // debug timeline
+    unsigned long long * trace = nullptr; int trace_next = 0; std::vector<int> trace_cls, trace_ctas;
+    // layer-slice pipeline over NCCL (see b200_pipeline_*)
+    void * nccl_comm = nullptr; int pp_rank = 0, pp_world = 1; float * d_final = nullptr;
 };
 
 namespace b200 {
@@ -105,15 +109,18 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set[s->device & 15] = true;
     }
-    a.NS = NS;
+    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pdl_early = env_int("B200_PDL_EARLY", 0); a.swp = env_int("B200_SWP", 0);
+    a.trace = nullptr;
+    if (s->trace && s->trace_next < 512) { a.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(s->cur_class); }
     int per_sm = s->opt_cta_per_sm > 0 ? s->opt_cta_per_sm : (int)(kSmemLimit / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 6) per_sm = 6;
     const int ncol = (a.N + NC - 1) / NC;
     int gx = a.W.n_tiles;
     const int cap = s->n_sm * per_sm;
     if (gx > cap) gx = cap;
     cudaLaunchConfig_t cfg{};
+    if (a.trace) s->trace_ctas.push_back(gx * ncol);
     cfg.gridDim = dim3(gx, ncol, 1);
     cfg.blockDim = dim3(RING ? kConsumers + 32 : kConsumers, 1, 1);
     cfg.dynamicSmemBytes = smem;
@@ -190,8 +197,10 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             f.W = Lw.f_v; f.y = s->qkv + 2 * E; if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
         } else {
             GemvArgs g{}; g.W = Lw.qkv; g.x = cur; g.ldx = E; g.norm_w = Lw.attn_norm; g.y = s->qkv; g.ldy = 3 * E;
-            g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu;
-            if ((rc = launch_gemv<1, PRO_NORM, EPI_STORE>(s, g))) return rc;
+            g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x;
+            // layers after the first get their input already normalised + quantised by the previous w2's last CTA
+            if (il > 0 && s->use_nq) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_STORE>(s, g))) return rc; }
+            else                     { if ((rc = launch_gemv<1, PRO_NORM, EPI_STORE>(s, g))) return rc; }
         }
         if (D == 128) {
             // head size 128: cluster kernel; for N = 1 RoPE + KV append are fused into its prologue
@@ -207,6 +216,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             if (N == 1) {
                 s->cur_class = 2;
                 aa.n0 = 0;
+                if (s->trace && s->trace_next < 512) { aa.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(2); s->trace_ctas.push_back(4 * H); }
                 if ((rc = launch_simple(s, k_attn128<true>, dim3(4 * H, 1, 1), dim3(256, 1, 1), asm_bytes, aa))) return rc;
             } else {
                 s->cur_class = 1;
@@ -246,17 +256,28 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             s->cur_class = 3;
             GemvArgs o{}; o.W = Lw.wo; o.x = s->att; o.ldx = E; o.resid = cur; o.ldr = E; o.y = s->ffin; o.ldy = E;
             o.N = N; o.out_rows = E; o.tsilu = s->tsilu; o.aq_in = s->aq_att; o.da_in = s->da_att;
-            if (D == 128) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, o))) return rc; }
-            else          { if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID>(s, o))) return rc; }
+            o.nq_norm_w = Lw.ffn_norm; o.nq_counter = s->nq_counter; o.aq_out = s->aq_x; o.da_out = s->da_x; o.out_nbq = s->nbqE; o.out_dscale = dsc;
+            if (D == 128) {
+                if (s->use_nq) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID_NQ>(s, o))) return rc; }
+                else           { if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, o))) return rc; }
+            } else {
+                if (s->use_nq) { if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID_NQ>(s, o))) return rc; }
+                else           { if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID>(s, o))) return rc; }
+            }
             s->cur_class = 4;
             GemvArgs g{}; g.W = Lw.w13; g.x = s->ffin; g.ldx = E; g.norm_w = Lw.ffn_norm; g.y = s->gate; g.ldy = FF;
-            g.N = N; g.out_rows = FF; g.tsilu = s->tsilu;
+            g.N = N; g.out_rows = FF; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x;
             g.aq_out = s->aq_gate; g.da_out = s->da_gate; g.out_nbq = s->nbqF; g.out_dscale = dsc;
-            if ((rc = launch_gemv<2, PRO_NORM, EPI_GATEQ>(s, g))) return rc;
+            if (s->use_nq) { if ((rc = launch_gemv<2, PRO_PREQ, EPI_GATEQ>(s, g))) return rc; }
+            else           { if ((rc = launch_gemv<2, PRO_NORM, EPI_GATEQ>(s, g))) return rc; }
             s->cur_class = 5;
             GemvArgs w{}; w.W = Lw.w2; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
             w.N = N; w.out_rows = E; w.tsilu = s->tsilu; w.aq_in = s->aq_gate; w.da_in = s->da_gate;
-            if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, w))) return rc;
+            if (il + 1 < s->L && s->use_nq) {
+                w.nq_norm_w = s->layers[il + 1].attn_norm; w.nq_counter = s->nq_counter; w.aq_out = s->aq_x; w.da_out = s->da_x;
+                w.out_nbq = s->nbqE; w.out_dscale = dsc;
+                if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID_NQ>(s, w))) return rc;
+            } else if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, w))) return rc;
         }
         cur = nxt;
     }
@@ -493,6 +514,10 @@ static int load_locked(b200_slice * s, const char * path) {
         const size_t nq = (size_t) s->n_ctx;
         if ((rc = dev_alloc(s, &s->aq_att, nq * s->nbqE * 32)) || (rc = dev_alloc(s, &s->da_att, nq * s->nbqE * 4)) ||
             (rc = dev_alloc(s, &s->aq_gate, nq * s->nbqF * 32)) || (rc = dev_alloc(s, &s->da_gate, nq * s->nbqF * 4))) return rc;
+        if ((rc = dev_alloc(s, &s->aq_x, nq * s->nbqE * 32)) || (rc = dev_alloc(s, &s->da_x, nq * s->nbqE * 4)) ||
+            (rc = dev_alloc(s, &s->nq_counter, nq))) return rc;
+        B200_CUDA(cudaMemset(s->aq_x, 0, nq * s->nbqE * 128)); B200_CUDA(cudaMemset(s->da_x, 0, nq * s->nbqE * 16));
+        B200_CUDA(cudaMemset(s->nq_counter, 0, nq * 4));
         B200_CUDA(cudaMemset(s->aq_att, 0, nq * s->nbqE * 128));  B200_CUDA(cudaMemset(s->da_att, 0, nq * s->nbqE * 16));
         B200_CUDA(cudaMemset(s->aq_gate, 0, nq * s->nbqF * 128)); B200_CUDA(cudaMemset(s->da_gate, 0, nq * s->nbqF * 16));
     }
@@ -502,6 +527,10 @@ static int load_locked(b200_slice * s, const char * path) {
     B200_CUDA(cudaMallocHost((void **) &s->h_in, (size_t) E * 4));
     B200_CUDA(cudaMallocHost((void **) &s->h_out, (size_t) E * 4));
     if ((rc = build_tables(s))) return rc;
+    if (env_int("B200_TRACE", 0)) {
+        if ((rc = dev_alloc(s, &s->trace, (size_t) 512 * 1024 * 8))) return rc;
+        B200_CUDA(cudaMemset(s->trace, 0, (size_t) 512 * 1024 * 8 * 8));
+    }
     B200_CUDA(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     B200_CUDA(cudaFuncSetAttribute(k_attn128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B200_CUDA(cudaFuncSetAttribute(k_attn128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -551,6 +580,7 @@ int b200_slice_load(const char * path, int device, int n_ctx, b200_slice_t ** ou
     s->use_ring  = env_int("B200_RING", 1) != 0;
     s->use_graph = env_int("B200_GRAPH", 1) != 0;
     s->use_pdl   = env_int("B200_PDL", 1) != 0;
+    s->use_nq    = env_int("B200_NQ", 0) != 0;   // last-CTA norm+quant epilogue: exact, but measured slower
     s->opt_ns = env_int("B200_NS", 0); s->opt_qs = env_int("B200_QS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0);
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
@@ -670,6 +700,18 @@ int b200_slice_profile_read(b200_slice_t * s, float * ms_by_class, int * launche
     return 0;
 }
 
+/* Debug timeline: when B200_TRACE=1 every matmul / attention launch of the NEXT captured graph (or un-graphed step)
+ * stamps %globaltimer per CTA: [0] entry, [1] after griddepcontrol.wait, [2] prologue done, [3] exit, [4] last weight copy issued. */
+int b200_debug_trace_read(b200_slice_t * s, unsigned long long * out, int * cls, int * ctas, int max_launches) {
+    if (!s || !s->trace) return 0;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    int n = s->trace_next < max_launches ? s->trace_next : max_launches;
+    cudaMemcpy(out, s->trace, (size_t) n * 1024 * 8 * 8, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; i++) { cls[i] = s->trace_cls[i]; ctas[i] = s->trace_ctas[i]; }
+    return n;
+}
+
 /* Test hook: copy `count` 32-bit words of an internal activation buffer to the host after a
  * forward (0 qkv, 1 att, 2 ffin, 3 gate, 4 xa, 5 xb, 6 q16, 7 k-cache, 8 v-cache). */
 int b200_debug_read(b200_slice_t * s, int which, size_t offset_words, size_t count, void * out) {
@@ -679,6 +721,123 @@ int b200_debug_read(b200_slice_t * s, int which, size_t offset_words, size_t cou
     B200_CUDA(cudaSetDevice(s->device));
     B200_CUDA(cudaStreamSynchronize(s->stream));
     B200_CUDA(cudaMemcpy(out, (const uint32_t *) src[which] + offset_words, count * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"
+
+
+// ============================================================================ layer-slice pipeline (NCCL)
+// The reference relays the activation between nodes through the client over TCP, one request per hop
+// (cli_api/common.py:148-154 -> control_center.py:224-244 -> routes.py:176-195).  For slices that live on the
+// GPUs of one NVSwitch box the hop is ONE ncclSend / ncclRecv of [n_tokens][n_embd] f32 on the slice's stream.
+// NCCL is bound at run time (dlopen) so that the single-GPU path carries no dependency on it.
+namespace b200 {
+struct NcclId { char bytes[128]; };
+struct NcclApi {
+    void * lib = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char * (*GetErrorString)(int) = nullptr;
+};
+static NcclApi & nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char * env = getenv("B200_NCCL_LIB");
+        const char * names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char * n : names) {
+            if (!n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId    = (int (*)(NcclId *)) dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank   = (int (*)(void **, int, NcclId, int)) dlsym(api.lib, "ncclCommInitRank");
+        api.Send           = (int (*)(const void *, size_t, int, int, void *, cudaStream_t)) dlsym(api.lib, "ncclSend");
+        api.Recv           = (int (*)(void *, size_t, int, int, void *, cudaStream_t)) dlsym(api.lib, "ncclRecv");
+        api.CommDestroy    = (int (*)(void *)) dlsym(api.lib, "ncclCommDestroy");
+        api.GetErrorString = (const char * (*)(int)) dlsym(api.lib, "ncclGetErrorString");
+    });
+    return api;
+}
+static int nccl_fail(const char * what, int rc) {
+    NcclApi & n = nccl();
+    return fail(B200_ENCCL, "%s failed: %s", what, n.GetErrorString ? n.GetErrorString(rc) : "NCCL error");
+}
+constexpr int kNcclFloat32 = 7;
+}  // namespace b200
+
+extern "C" {
+
+int b200_pipeline_unique_id(void * id128) {
+    NcclApi & n = nccl();
+    if (!n.lib || !n.GetUniqueId) return fail(B200_ENCCL, "libnccl.so.2 not found (set B200_NCCL_LIB)");
+    if (!id128) return fail(B200_EINVAL, "null id buffer");
+    NcclId id;
+    int rc = n.GetUniqueId(&id);
+    if (rc) return nccl_fail("ncclGetUniqueId", rc);
+    memcpy(id128, id.bytes, 128);
+    return 0;
+}
+
+int b200_pipeline_init(b200_slice_t * s, int rank, int nranks, const void * id128) {
+    if (!s || !id128 || rank < 0 || rank >= nranks) return fail(B200_EINVAL, "bad pipeline arguments");
+    NcclApi & n = nccl();
+    if (!n.lib || !n.CommInitRank) return fail(B200_ENCCL, "libnccl.so.2 not found (set B200_NCCL_LIB)");
+    std::lock_guard<std::mutex> lk(s->mu);
+    B200_CUDA(cudaSetDevice(s->device));
+    NcclId id; memcpy(id.bytes, id128, 128);
+    int rc = n.CommInitRank(&s->nccl_comm, nranks, id, rank);
+    if (rc) return nccl_fail("ncclCommInitRank", rc);
+    s->pp_rank = rank; s->pp_world = nranks;
+    if (rank == 0 && !s->d_final) { int e = dev_alloc(s, &s->d_final, (size_t) s->n_ctx * s->E); if (e) return e; }
+    return 0;
+}
+
+int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int ring) {
+    if (!s || !s->nccl_comm) return fail(B200_EINVAL, "pipeline not initialised");
+    NcclApi & n = nccl();
+    std::lock_guard<std::mutex> lk(s->mu);
+    B200_CUDA(cudaSetDevice(s->device));
+    const size_t count = (size_t) n_tokens * s->E;
+    const int r = s->pp_rank, W = s->pp_world;
+    int rc;
+    const float * in = d_in;
+    if (r > 0) {
+        if ((rc = n.Recv(s->d_in, count, kNcclFloat32, r - 1, s->nccl_comm, s->stream))) return nccl_fail("ncclRecv", rc);
+        in = s->d_in;
+    } else if (!in) return fail(B200_EINVAL, "rank 0 needs an input buffer");
+    if ((rc = forward_locked(s, in, n_tokens, s->d_out, false))) return rc;
+    if (r < W - 1) {
+        if ((rc = n.Send(s->d_out, count, kNcclFloat32, r + 1, s->nccl_comm, s->stream))) return nccl_fail("ncclSend", rc);
+    } else if (ring && W > 1) {
+        if ((rc = n.Send(s->d_out, count, kNcclFloat32, 0, s->nccl_comm, s->stream))) return nccl_fail("ncclSend", rc);
+    }
+    if (r == 0 && ring && W > 1) {
+        // the last slice's output comes back to the first rank (where the client-side lm_head lives)
+        if ((rc = n.Recv(s->d_final, count, kNcclFloat32, W - 1, s->nccl_comm, s->stream))) return nccl_fail("ncclRecv", rc);
+    }
+    s->launches += (r > 0) + (r < W - 1 || (ring && W > 1)) + (r == 0 && ring && W > 1);
+    return 0;
+}
+
+/* Device pointer of the pipeline's final activation on rank 0 (valid after a `ring` step), else dev_out. */
+float * b200_pipeline_result(b200_slice_t * s) { return s ? (s->pp_world > 1 && s->pp_rank == 0 && s->d_final ? s->d_final : s->d_out) : nullptr; }
+
+int b200_pipeline_destroy(b200_slice_t * s) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->nccl_comm) {
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->stream);
+        NcclApi & n = nccl();
+        if (n.CommDestroy) n.CommDestroy(s->nccl_comm);
+        s->nccl_comm = nullptr; s->pp_world = 1; s->pp_rank = 0;
+    }
     return 0;
 }
 

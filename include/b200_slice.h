@@ -118,8 +118,10 @@ int b200_pipeline_init(b200_slice_t * s, int rank, int nranks, const void * id12
 /* One pipeline step on this rank: rank 0 takes `d_in` (device, may be NULL on other ranks), every
  * rank r>0 receives [n_tokens][n_embd] from r-1, runs its layers, and sends to r+1; the last rank
  * leaves the result in its dev_out buffer and, when `ring` != 0, also sends it to rank 0 (which
- * receives it into its dev_out), closing the token loop. Asynchronous on the slice's stream. */
+ * receives it into the buffer b200_pipeline_result() returns), closing the token loop. Asynchronous on the slice's stream. */
 int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int ring);
+/* Device pointer of the pipeline's final activation: on rank 0 after a ring step the last slice's output, else dev_out. */
+float * b200_pipeline_result(b200_slice_t * s);
 int b200_pipeline_destroy(b200_slice_t * s);
 
 /* ---- client-side extra layers (tok_embeddings / norm / output), next-row N1 ------------ */

@@ -1,0 +1,32 @@
+"""Timeline of one graphed decode step from in-kernel %globaltimer stamps (B200_TRACE=1)."""
+import os, sys, ctypes as C
+os.environ["B200_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from distributedllm_b200 import capi
+import bench
+L = int(os.environ.get("PROF_LAYERS", "4"))
+path = bench.slice_file("7b", 0, L - 1)
+sl = capi.Slice(path, 0, 512)
+xp = bench.synth_inputs(256, sl.n_embd, 1)
+for i in range(0, 256, 64):
+    sl.forward(xp[i:i + 64])
+bench._h2d(sl, xp[0:1])
+for i in range(6):
+    sl.forward_device(sl.dev_in, 1, sl.dev_out)
+sl.sync()
+lib = capi.lib()
+buf = np.zeros((512, 1024, 8), np.uint64); cls = np.zeros(512, np.int32); ctas = np.zeros(512, np.int32)
+lib.b200_debug_trace_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+n = lib.b200_debug_trace_read(sl.handle, buf.ctypes.data, cls.ctypes.data, ctas.ctypes.data, 512)
+names = ["qkv", "rope", "attn", "wo", "w13", "w2", "adv"]
+# the decode graph's launches are the LAST 5*L entries
+first = n - 5 * L
+t_base = None
+print("launch  kernel  ctas | first_start last_start | first_ready(dep) | prologue_done(max) | last_copy_issued(max) | end(max)   [us from step start]")
+for i in range(first, n):
+    k = ctas[i]; d = buf[i, :k].astype(np.int64)
+    if t_base is None: t_base = d[:, 0].min()
+    f = lambda col, fn: (fn(d[:, col][d[:, col] > 0]) - t_base) / 1e3 if (d[:, col] > 0).any() else float("nan")
+    print("%3d %6s %5d | %8.2f %8.2f | %8.2f | %8.2f | %8.2f | %8.2f" % (i - first, names[cls[i]], k, f(0, np.min), f(0, np.max), f(1, np.min), f(2, np.max), f(4, np.max), f(3, np.max)))
+sl.close()

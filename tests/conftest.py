@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# the C oracle uses OpenMP over matmul rows; on a 128-core GPU box the fork/join cost of 128 threads dwarfs the
+# tiny test models, so cap it (results do not depend on the thread count)
+os.environ.setdefault("OMP_NUM_THREADS", "8")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -59,7 +59,7 @@ def test_ring_and_simple_kernels_agree(tmp_models, monkeypatch):
 def test_decode_only_long(tmp_models, shape):
     sh = ggjt.SHAPES[shape]
     path = tmp_models(shape, ggjt.T_Q4_0, 0, 2)
-    bad, tot = _run_pair(path, [1] * 70, sh)
+    bad, tot = _run_pair(path, [1] * 40, sh)
     assert bad == 0
 
 
