@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from distributedllm_b200 import ggjt  # noqa: E402
+from distributedllm_b200.pipeline import layer_ranges  # noqa: E402
 
 METRIC = "decode tokens/sec LLaMA-7B Q4_0 seq512 bs1"
 UNIT = "tokens/s"
@@ -58,16 +59,6 @@ def slice_file(shape_name: str, a: int, b: int) -> str:
         ggjt.write_fast_q4_slice(tmp, sh, a, b, SEED)
         os.replace(tmp, p)
     return p
-
-
-def layer_ranges(n_layer: int, n: int):
-    base, extra = divmod(n_layer, n)
-    out, a = [], 0
-    for r in range(n):
-        k = base + (1 if r < extra else 0)
-        out.append((a, a + k - 1))
-        a += k
-    return out
 
 
 def synth_inputs(n: int, n_embd: int, seed: int) -> np.ndarray:

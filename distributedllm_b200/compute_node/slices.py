@@ -1,0 +1,112 @@
+"""Slice container of a compute node (reference: distllm/compute_node/slices.py:5-95).
+
+`SliceContainer.load / forward / clear_context` keep the reference's semantics:
+  * metadata {'format': 'test'} selects the two-byte `DummySlice` (k, b) -> k*x + b used by handler tests
+    (slices.py:19-26, 64-71);
+  * anything else is a GGJT slice file run on the GPU by `GGMLSlice` through the `llm` module
+    (slices.py:74-91): llm.load_slice(path); llm.propagate_forward(values); llm.clear_context() != 0 raises.
+A non-list result of llm.propagate_forward (the module returns an int status when the eval fails,
+tensor_processor.cpp:2148-2151) raises NeuralComputationError, which the route maps to
+`neural_computation_error`.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from dataclasses import dataclass
+from typing import Any, Optional
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def import_llm():
+    """The `llm` extension is built in-tree next to libb200slice.so; make it importable by its bare name,
+    the way the reference's Dockerfile does with PYTHONPATH=/libs."""
+    if _PKG_DIR not in sys.path:
+        sys.path.insert(0, _PKG_DIR)
+    import llm
+    if not hasattr(llm, "propagate_forward"):
+        raise ImportError("the imported `llm` module is not the slice runtime")
+    return llm
+
+
+@dataclass
+class Tensor:
+    shape: tuple
+    values: Any            # list[float] on the reference wire; numpy float32 also accepted
+
+
+class SliceNotLoadedError(Exception):
+    pass
+
+
+class NeuralComputationError(Exception):
+    pass
+
+
+class ModelSlice:
+    def __call__(self, tensor: Tensor) -> Tensor:
+        raise NotImplementedError
+
+    def clear_context(self) -> None:
+        pass
+
+
+class DummySlice(ModelSlice):
+    def __init__(self, k, b):
+        self.k, self.b = k, b
+
+    def __call__(self, tensor: Tensor) -> Tensor:
+        return Tensor(tensor.shape, [self.k * v + self.b for v in tensor.values])
+
+
+class GGMLSlice(ModelSlice):
+    """A reference-format slice file resident on the GPU."""
+
+    def __init__(self, file_path: str):
+        self.path = file_path
+        self.llm = import_llm()
+        self.llm.load_slice(self.path)
+
+    def __call__(self, tensor: Tensor) -> Tensor:
+        out = self.llm.propagate_forward(tensor.values)
+        if not isinstance(out, list):
+            raise NeuralComputationError("slice forward failed with status %r" % (out,))
+        return Tensor(tensor.shape, out)
+
+    def clear_context(self) -> None:
+        if self.llm.clear_context() != 0:
+            raise Exception("Error occurred when clearing context")
+
+
+class SliceContainer:
+    def __init__(self, fs_backend):
+        self.fs_backend = fs_backend
+        self.slice: Optional[ModelSlice] = None
+        self.metadata = None
+
+    def load(self, slice_path, metadata) -> None:
+        self.metadata = metadata
+        if metadata.get("format") == "test":
+            with self.fs_backend.open_file(slice_path, mode="rb") as f:
+                data = f.read()
+            self.slice = DummySlice(data[0], data[1])
+        else:
+            self.slice = GGMLSlice(slice_path)
+
+    def forward(self, tensor: Tensor) -> Tensor:
+        if self.slice is None:
+            raise SliceNotLoadedError()
+        return self.slice(tensor)
+
+    def clear_context(self) -> None:
+        if self.slice is not None:
+            self.slice.clear_context()
+
+    @property
+    def info(self):
+        return self.metadata
+
+    @property
+    def is_loaded(self) -> bool:
+        return self.slice is not None

@@ -842,3 +842,246 @@ int b200_pipeline_destroy(b200_slice_t * s) {
 }
 
 }  // extern "C"
+
+// ============================================================================ client-side extra layers (N1)
+// tok_embeddings lookup, final RMSNorm + lm_head, argmax, tokenizer -- resident, instead of the reference
+// re-opening and re-reading the extra-layers file on every call (tensor_processor.cpp:1717-1908, 2033-2057,
+// 2219-2235).  The lm_head is the same exact-mode weight matmul as the slice layers (RMSNorm prologue fused).
+#include <queue>
+#include <unordered_map>
+
+struct b200_extra {
+    b200_slice ctx;                       // device / stream / launch plumbing shared with the slice kernels
+    int n_vocab = 0, E = 0, emb_type = 0, out_type = 0;
+    uint8_t * emb_raw = nullptr;          // tok_embeddings as stored (row = token)
+    float * norm_w = nullptr;
+    PackedW out{}; uint16_t * out_f16 = nullptr;
+    float * d_x = nullptr, * d_logits = nullptr; int32_t * d_tok = nullptr; int cap_tokens = 0;
+    std::vector<std::pair<std::string, float>> vocab;
+    std::unordered_map<std::string, int> token_to_id;
+    std::mutex mu;
+};
+
+namespace b200 {
+
+__global__ void k_embed_rows(const uint8_t * emb, int type, int E, const int32_t * tok, int n_vocab, float * out) {
+    const int n = blockIdx.y, t = tok[n];
+    float * dst = out + (size_t) n * E;
+    if (t < 0 || t >= n_vocab) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E; i += gridDim.x * blockDim.x) dst[i] = 0.f; return; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < E; i += gridDim.x * blockDim.x) {
+        float v;
+        if (type == kWT_Q4_0) {                      // dequantize_row_q4_0, ggml.c:1523-1541
+            const uint8_t * blk = emb + ((size_t) t * (E / 32) + i / 32) * 18;
+            const float d = h2f(*(const uint16_t *) blk);
+            const int j = i & 31, q = blk[2 + (j & 15)];
+            v = fmul((float)((j < 16 ? (q & 0x0F) : (q >> 4)) - 8), d);
+        } else if (type == kWT_Q8_0) {
+            const uint8_t * blk = emb + ((size_t) t * (E / 32) + i / 32) * 34;
+            v = fmul((float)((const int8_t *)(blk + 2))[i & 31], h2f(*(const uint16_t *) blk));
+        } else if (type == kWT_F16) v = h2f(((const uint16_t *) emb)[(size_t) t * E + i]);
+        else v = ((const float *) emb)[(size_t) t * E + i];
+        dst[i] = v;
+    }
+}
+
+static int extra_reserve(b200_extra * e, int n) {
+    if (n <= e->cap_tokens) return 0;
+    b200_slice * s = &e->ctx;
+    int rc;
+    if ((rc = dev_alloc(s, &e->d_x, (size_t) n * e->E)) || (rc = dev_alloc(s, &e->d_logits, (size_t) n * e->n_vocab)) ||
+        (rc = dev_alloc(s, &e->d_tok, (size_t) n))) return rc;
+    e->cap_tokens = n;
+    return 0;
+}
+
+// sentencepiece-style greedy bigram merging, as tensor_processor.cpp:1596-1714 specifies it:
+// start from UTF-8 characters, repeatedly merge the adjacent pair whose concatenation is the vocabulary
+// entry with the highest score (ties: leftmost), then map pieces to ids, unknown pieces to byte ids (+3).
+static void tokenize_pieces(const b200_extra & e, const std::string & text, std::vector<int32_t> & out) {
+    struct Piece { int prev, next; size_t off, len; };
+    struct Cand { float score; int left, right; size_t len; };
+    struct Worse { bool operator()(const Cand & a, const Cand & b) const { return a.score < b.score || (a.score == b.score && a.left > b.left); } };
+    std::vector<Piece> ps;
+    for (size_t off = 0; off < text.size();) {
+        static const size_t lens[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 4};
+        size_t n = std::min(text.size() - off, lens[(uint8_t) text[off] >> 4]);
+        const int idx = (int) ps.size();
+        ps.push_back({idx - 1, off + n == text.size() ? -1 : idx + 1, off, n});
+        off += n;
+    }
+    std::priority_queue<Cand, std::vector<Cand>, Worse> heap;
+    auto offer = [&](int l, int r) {
+        if (l < 0 || r < 0) return;
+        const std::string joined = text.substr(ps[l].off, ps[l].len + ps[r].len);
+        auto it = e.token_to_id.find(joined);
+        if (it == e.token_to_id.end() || (size_t) it->second >= e.vocab.size()) return;
+        heap.push({e.vocab[it->second].second, l, r, joined.size()});
+    };
+    for (int i = 1; i < (int) ps.size(); i++) offer(i - 1, i);
+    while (!heap.empty()) {
+        const Cand c = heap.top(); heap.pop();
+        Piece & L = ps[c.left]; Piece & R = ps[c.right];
+        if (L.len == 0 || R.len == 0 || L.len + R.len != c.len) continue;      // stale candidate
+        L.len += R.len; R.len = 0;
+        L.next = R.next;
+        if (R.next >= 0) ps[R.next].prev = c.left;
+        offer(L.prev, c.left);
+        offer(c.left, L.next);
+    }
+    for (int i = ps.empty() ? -1 : 0; i != -1; i = ps[i].next) {
+        auto it = e.token_to_id.find(text.substr(ps[i].off, ps[i].len));
+        if (it != e.token_to_id.end()) out.push_back(it->second);
+        else for (size_t j = 0; j < ps[i].len; j++) out.push_back((int32_t)(uint8_t) text[ps[i].off + j] + 3);
+    }
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int b200_extra_load(const char * path, int device, b200_extra_t ** out) {
+    if (!path || !out) return fail(B200_EINVAL, "b200_extra_load: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B200_ENODEV, "no CUDA device visible: no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200_ENODEV, "device %d out of range", device);
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(B200_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    B200_CUDA(cudaSetDevice(device));
+    std::unique_ptr<GgjtFile> fp;
+    try { fp.reset(new GgjtFile(path, true)); }
+    catch (const std::exception & ex) { return fail(B200_EFILE, "error loading extra layers: %s", ex.what()); }
+    GgjtFile & f = *fp;
+    std::unique_ptr<b200_extra> e(new b200_extra());
+    b200_slice * s = &e->ctx;
+    s->device = device; s->n_sm = prop.multiProcessorCount;
+    s->use_pdl = false; s->use_graph = false;
+    B200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    e->n_vocab = (int) f.n_vocab; e->E = (int) f.n_embd;
+    const uint32_t E = f.n_embd, V = f.n_vocab;
+    int rc;
+    try {
+        const GgjtTensor & te = f.get("tok_embeddings.weight", {E, V});
+        const GgjtTensor & tn = f.get("norm.weight", {E});
+        const GgjtTensor & to = f.get("output.weight", {E, V});
+        e->emb_type = (int) te.type; e->out_type = (int) to.type;
+        if (te.type != GT_Q4_0 && te.type != GT_Q8_0 && te.type != GT_F16 && te.type != GT_F32)
+            return fail(B200_EFILE, "tok_embeddings type %u unsupported", te.type);
+        if (to.type != GT_Q4_0 && to.type != GT_Q8_0 && to.type != GT_F16)
+            return fail(B200_EFILE, "output.weight type %u unsupported (Q4_0, Q8_0, F16; the Q6_K lm_head llama.cpp's quantize writes for "
+                                    "n_embd %% 256 == 0 is not implemented yet)", to.type);
+        if (tn.type != GT_F32) return fail(B200_EFILE, "norm.weight must be F32");
+        if ((rc = dev_alloc(s, &e->emb_raw, te.nbytes)) || (rc = dev_alloc(s, &e->norm_w, (size_t) E))) return rc;
+        B200_CUDA(cudaMemcpyAsync(e->emb_raw, f.data(te), te.nbytes, cudaMemcpyHostToDevice, s->stream));
+        B200_CUDA(cudaMemcpyAsync(e->norm_w, f.data(tn), (size_t) E * 4, cudaMemcpyHostToDevice, s->stream));
+        uint8_t * scratch = nullptr;
+        B200_CUDA(cudaMalloc((void **) &scratch, to.nbytes + 4096));
+        if (to.type == GT_F16) rc = pack_f16(s, f, to, scratch, &e->out_f16);
+        else { const GgjtTensor * src[1] = {&to}; rc = pack_matrix(s, f, src, 1, 0, 1, scratch, &e->out); }
+        B200_CUDA(cudaStreamSynchronize(s->stream));
+        cudaFree(scratch);
+        if (rc) return rc;
+    } catch (const std::exception & ex) { return fail(B200_EFILE, "error loading extra layers: %s", ex.what()); }
+    // fp16 SiLU table is not needed here, but the launch helper wants events
+    B200_CUDA(cudaEventCreate(&s->ev0));
+    B200_CUDA(cudaEventCreate(&s->ev1));
+    e->vocab = std::move(f.vocab);
+    for (int i = 0; i < (int) e->vocab.size(); i++) e->token_to_id[e->vocab[i].first] = i;
+    *out = e.release();
+    return 0;
+}
+
+int b200_extra_unload(b200_extra_t * e) {
+    if (!e) return fail(B200_EINVAL, "null handle");
+    b200_slice * s = &e->ctx;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (void * p : s->allocs) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (cudaEvent_t ev : s->prof_ev) cudaEventDestroy(ev);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete e;
+    return 0;
+}
+
+int b200_extra_dims(b200_extra_t * e, int * n_vocab, int * n_embd) {
+    if (!e) return fail(B200_EINVAL, "null handle");
+    if (n_vocab) *n_vocab = e->n_vocab;
+    if (n_embd) *n_embd = e->E;
+    return 0;
+}
+
+int b200_extra_embed(b200_extra_t * e, const int32_t * tokens, int n_tokens, float * out) {
+    if (!e || !tokens || !out || n_tokens <= 0) return fail(B200_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    b200_slice * s = &e->ctx;
+    B200_CUDA(cudaSetDevice(s->device));
+    int rc = extra_reserve(e, n_tokens);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(e->d_tok, tokens, (size_t) n_tokens * 4, cudaMemcpyHostToDevice, s->stream));
+    k_embed_rows<<<dim3((e->E + 255) / 256, n_tokens), 256, 0, s->stream>>>(e->emb_raw, e->emb_type, e->E, e->d_tok, e->n_vocab, e->d_x);
+    B200_CUDA(cudaGetLastError());
+    s->launches++;
+    B200_CUDA(cudaMemcpyAsync(out, e->d_x, (size_t) n_tokens * e->E * 4, cudaMemcpyDeviceToHost, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int extra_logits_device(b200_extra * e, const float * emb, int n_tokens) {
+    b200_slice * s = &e->ctx;
+    int rc = extra_reserve(e, n_tokens);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(e->d_x, emb, (size_t) n_tokens * e->E * 4, cudaMemcpyHostToDevice, s->stream));
+    if (e->out_type == kWT_F16) {
+        GemvF16Args f{}; f.K = e->E; f.x = e->d_x; f.ldx = e->E; f.norm_w = e->norm_w; f.N = n_tokens;
+        f.rows = e->n_vocab; f.W = e->out_f16; f.y = e->d_logits; f.ldy = e->n_vocab;
+        return launch_f16<PRO_NORM, EPI_STORE>(s, f);
+    }
+    GemvArgs g{}; g.W = e->out; g.x = e->d_x; g.ldx = e->E; g.norm_w = e->norm_w; g.y = e->d_logits; g.ldy = e->n_vocab;
+    g.N = n_tokens; g.out_rows = e->n_vocab;
+    return launch_gemv<1, PRO_NORM, EPI_STORE>(s, g);
+}
+
+int b200_extra_logits(b200_extra_t * e, const float * emb, int n_tokens, int all_logits, float * out) {
+    if (!e || !emb || !out || n_tokens <= 0) return fail(B200_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    b200_slice * s = &e->ctx;
+    B200_CUDA(cudaSetDevice(s->device));
+    int rc = extra_logits_device(e, emb, n_tokens);
+    if (rc) return rc;
+    const size_t V = (size_t) e->n_vocab;
+    if (all_logits) B200_CUDA(cudaMemcpyAsync(out, e->d_logits, (size_t) n_tokens * V * 4, cudaMemcpyDeviceToHost, s->stream));
+    else B200_CUDA(cudaMemcpyAsync(out, e->d_logits + (size_t)(n_tokens - 1) * V, V * 4, cudaMemcpyDeviceToHost, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int b200_extra_next_token(b200_extra_t * e, const float * emb, int n_tokens, int32_t * token) {
+    if (!e || !emb || !token || n_tokens <= 0) return fail(B200_EINVAL, "bad argument");
+    std::vector<float> logits((size_t) e->n_vocab);
+    int rc = b200_extra_logits(e, emb, n_tokens, 0, logits.data());
+    if (rc) return rc;
+    float best = -(1000000000000.0f); int32_t id = 0;          // sample_next_token, tensor_processor.cpp:1894-1908
+    for (size_t i = 0; i < logits.size(); i++) if (logits[i] > best) { best = logits[i]; id = (int32_t) i; }
+    *token = id;
+    return 0;
+}
+
+int b200_extra_tokenize(b200_extra_t * e, const char * prompt, int32_t * out, int cap) {
+    if (!e || !prompt) return -B200_EINVAL;
+    const std::string text(prompt);
+    std::vector<int32_t> ids;
+    if (!text.empty()) { ids.push_back(1); tokenize_pieces(*e, text, ids); }      // BOS = 1 (llama_token_bos)
+    for (int i = 0; i < (int) ids.size() && i < cap && out; i++) out[i] = ids[i];
+    return (int) ids.size();
+}
+
+const char * b200_extra_token_text(b200_extra_t * e, int32_t id, int * len) {
+    if (!e || id < 0 || id >= (int32_t) e->vocab.size()) { if (len) *len = 0; return nullptr; }
+    if (len) *len = (int) e->vocab[id].first.size();
+    return e->vocab[id].first.data();
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+"""Compute-node handlers, uploads and the RPC client against an in-process TCP server -- the reference's
+tests/unit/test_compute_node.py / test_control_center.py scenarios, with the DummySlice (k*x + b) standing in
+for the model (slices.py:19-26, 64-71 of the reference)."""
+import hashlib
+import io
+import json
+import threading
+
+import pytest
+
+from distributedllm_b200 import protocol
+from distributedllm_b200.compute_node import serve
+from distributedllm_b200.compute_node.routes import routes
+from distributedllm_b200.compute_node.tcp_handler import RequestContext
+from distributedllm_b200.control_center import Connection, OperationFailedError
+
+
+def _upload(ctx, data: bytes, meta: dict, checksum=None) -> int:
+    sid = routes["request_file_submission_begin"](ctx, protocol.RequestFileSubmissionBegin(json.dumps(meta))).submission_id
+    for i in range(0, len(data), 3):
+        r = routes["request_submit_part"](ctx, protocol.RequestSubmitPart(sid, i // 3, data[i:i + 3]))
+        assert r.part_size == len(data[i:i + 3])
+    return sid, routes["request_file_submission_end"](ctx, protocol.RequestFileSubmissionEnd(
+        sid, checksum or hashlib.sha256(data).hexdigest()))
+
+
+def test_status_brand_new_then_up():
+    ctx = RequestContext.default(names=["a", "b"])
+    assert json.loads(routes["status_request"](ctx, protocol.RequestStatus()).status_json) == {"status": "brand_new"}
+    meta = {"type": "slice", "model": "m", "layer_from": 0, "layer_to": 3, "format": "test"}
+    _, end = _upload(ctx, bytes([2, 5]), meta)
+    assert (end.file_name, end.total_size) == ("a", 2)
+    loaded = routes["load_slice_request"](ctx, protocol.RequestLoadSlice(name="a"))
+    assert (loaded.name, loaded.model) == ("a", "m")
+    st = json.loads(routes["status_request"](ctx, protocol.RequestStatus()).status_json)
+    assert st["status"] == "up" and st["metadata"] == meta
+
+
+def test_propagate_forward_dummy_slice_and_errors():
+    ctx = RequestContext.default(names=["a"])
+    req = protocol.RequestPropagateForward(2, 2, [1.0, 2.0, 3.0, 4.0])
+    r = routes["propagate_forward_request"](ctx, req)
+    assert (r.msg, r.error, r.operation) == ("operation_failure", "slice_not_loaded", "propagate_forward_request")
+    _upload(ctx, bytes([3, 1]), {"type": "slice", "model": "m", "layer_from": 0, "layer_to": 0, "format": "test"})
+    routes["load_slice_request"](ctx, protocol.RequestLoadSlice(name="a"))
+    r = routes["propagate_forward_request"](ctx, req)
+    assert (r.msg, r.axis0, r.axis1, r.values) == ("tensor_response", 2, 2, [4.0, 7.0, 10.0, 13.0])
+    assert routes["clear_context_request"](ctx, protocol.RequestClearContext()).msg == "clear_context_response"
+    bad = RequestContext.with_failing_loader(names=["a"])
+    assert routes["propagate_forward_request"](bad, req).error == "neural_computation_error"
+
+
+def test_load_slice_failures():
+    ctx = RequestContext.with_failing_loader(names=["a"])
+    assert routes["load_slice_request"](ctx, protocol.RequestLoadSlice(name="nope")).error == "slice_not_found"
+    _upload(ctx, b"xy", {"type": "slice", "model": "m", "layer_from": 0, "layer_to": 0, "format": "test"})
+    assert routes["load_slice_request"](ctx, protocol.RequestLoadSlice(name="a")).error == "slice_load_error"
+
+
+def test_upload_state_machine():
+    ctx = RequestContext.default(names=["a", "b"])
+    begin = protocol.RequestFileSubmissionBegin(json.dumps({"type": "any"}))
+    sid = routes["request_file_submission_begin"](ctx, begin).submission_id
+    assert routes["request_file_submission_begin"](ctx, begin).error == "parallel_upload_forbidden"
+    assert routes["request_submit_part"](ctx, protocol.RequestSubmitPart(sid + 5, 0, b"z")).error == "upload_not_found"
+    assert routes["request_file_submission_end"](ctx, protocol.RequestFileSubmissionEnd(sid + 5, "0")).error == "upload_not_found"
+    routes["request_submit_part"](ctx, protocol.RequestSubmitPart(sid, 0, b"hello"))
+    assert routes["request_file_submission_end"](ctx, protocol.RequestFileSubmissionEnd(sid, "deadbeef")).error == "file_upload_failed"
+    assert ctx.registry.failed == [sid] and ctx.registry.in_progress == []
+    # non-slice uploads are not listed as slices
+    _upload(ctx, b"abc", {"type": "any"})
+    assert json.loads(routes["slices_request"](ctx, protocol.RequestAllSlices()).slices_json) == []
+
+
+@pytest.fixture()
+def node(tmp_path):
+    import distributedllm_b200.compute_node.tcp_handler as th
+    th._PROD = None
+    srv = serve.make_server("127.0.0.1", 0, str(tmp_path / "uploads"))
+    t = threading.Thread(target=srv.serve_forever, daemon=True)
+    t.start()
+    yield Connection(("127.0.0.1", srv.server_address[1])), srv
+    srv.shutdown()
+    srv.server_close()
+    th._PROD = None
+
+
+def test_client_against_live_node(node, tmp_path):
+    conn, _ = node
+    assert conn.get_status() == {"status": "brand_new"}
+    with pytest.raises(OperationFailedError):
+        conn.propagate_forward([1.0], (1, 1))
+    res = conn.push_slice(io.BytesIO(bytes([2, 1])), "toy", {"layer_from": 4, "layer_to": 7, "format": "test"}, chunk_size=1)
+    assert res == {"file_name": "orb", "total_size": 2}
+    assert conn.list_all_slices() == [{"name": "orb", "model": "toy", "layer_from": 4, "layer_to": 7}]
+    with pytest.raises(OperationFailedError):
+        conn.load_slice("missing")
+    assert conn.load_slice("orb") == {"name": "orb", "model": "toy"}
+    out = conn.propagate_forward([0.5, -1.0, 2.0], (1, 3))
+    assert out == {"shape": [1, 3], "values": [2.0, -1.0, 5.0]}
+    assert conn.clear_context() == {}
+    # registry persisted for the next start
+    state = json.load(open(tmp_path / "uploads" / "registry_data.json"))
+    assert state["finished"] == [0]
+
+
+def test_shape_mismatch_is_an_error(node, monkeypatch):
+    conn, _ = node
+    conn.push_slice(io.BytesIO(bytes([1, 0])), "toy", {"layer_from": 0, "layer_to": 0, "format": "test"})
+    conn.load_slice("orb")
+    real = conn._get_response
+
+    def lie(request, sock=None):
+        r = real(request, sock)
+        if r.msg == "tensor_response":
+            r.axis1 += 1
+        return r
+    monkeypatch.setattr(conn, "_get_response", lie)
+    with pytest.raises(OperationFailedError):
+        conn.propagate_forward([1.0, 2.0], (1, 2))

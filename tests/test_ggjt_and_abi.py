@@ -1,0 +1,104 @@
+"""Slice-file format library and the C-ABI surface (no GPU: the library must LOAD and export every symbol
+include/b200_slice.h declares, and fail loudly -- not fall back -- when there is no device)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from distributedllm_b200 import ggjt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_q4_0_quantizer_layout_and_roundtrip():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((4, 64)).astype(np.float32)
+    q = ggjt.quantize_q4_0(x)
+    assert q.shape == (4, 2, 18)
+    d = q[..., :2].copy().view(np.float16).astype(np.float32)[..., 0]
+    xb = x.reshape(4, 2, 32)
+    idx = np.abs(xb).argmax(2)
+    mx = np.take_along_axis(xb, idx[..., None], 2)[..., 0]
+    assert np.array_equal(d, (mx / np.float32(-8)).astype(np.float16).astype(np.float32))   # d = max / -8 (ggml.c:957)
+    y = ggjt.dequantize_q4_0(q)
+    assert np.sqrt(np.mean((x - y) ** 2)) < 0.12         # vendor test-quantize-fns.cpp bounds the same RMSE for unit Gaussians
+    # the element with the largest magnitude maps to nibble 0 (-8 * d)
+    lo = (q[..., 2:] & 0x0F).astype(int); hi = (q[..., 2:] >> 4).astype(int)
+    nib = np.concatenate([lo, hi], 2)
+    assert (np.take_along_axis(nib, idx[..., None], 2)[..., 0] == 0).all()
+
+
+def test_slice_file_roundtrip(tmp_path):
+    sh = ggjt.SHAPES["tiny"]
+    p = str(tmp_path / "s.bin")
+    ggjt.write_synth_slice(p, sh, 1, 2, ggjt.T_Q4_0, seed=0)
+    f = ggjt.read_file(p)
+    hp = f.hparams
+    assert (hp.n_embd, hp.n_head, hp.n_layer, hp.first_layer, hp.ftype, hp.n_ff) == (256, 4, 2, 1, ggjt.FTYPE_Q4_0, 704)
+    assert len(f.tensors) == 18 and len(f.vocab) == 512
+    t = f.tensors["layers.2.feed_forward.w2.weight"]
+    assert t.ne == (704, 256) and t.ttype == ggjt.T_Q4_0 and t.offset % 32 == 0 and t.nbytes == 704 * 256 // 32 * 18
+    assert f.tensors["layers.1.attention_norm.weight"].ttype == ggjt.T_F32
+
+
+def test_slicer_equals_direct_writer(tmp_path):
+    sh = ggjt.SHAPES["tiny"]
+    full, a, b, e1, e2 = (str(tmp_path / n) for n in ("full.bin", "a.bin", "b.bin", "e1.bin", "e2.bin"))
+    ggjt.write_synth_full(full, sh, ggjt.T_Q4_0, seed=0)
+    ggjt.slice_model(full, a, 1, 2)
+    ggjt.write_synth_slice(b, sh, 1, 2, ggjt.T_Q4_0, seed=0)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    ggjt.extract_extra_layers(full, e1)
+    ggjt.write_synth_extra(e2, sh, ggjt.T_Q4_0, seed=0)
+    assert open(e1, "rb").read() == open(e2, "rb").read()
+    assert ggjt.read_file(e1).hparams.first_layer == ggjt.NO_FIRST_LAYER
+
+
+def test_fast_generator_writes_a_loadable_slice(tmp_path):
+    from oracle import oracle
+    sh = ggjt.ModelShape(512, 256, 32, 2, 2)
+    p = str(tmp_path / "fast.bin")
+    n = ggjt.write_fast_q4_slice(p, sh, 0, 1, seed=0)
+    assert n == os.path.getsize(p)
+    s = oracle.PortSlice(p, 32)
+    y = s.forward(np.random.default_rng(0).standard_normal((3, 256), dtype=np.float32))
+    assert np.isfinite(y).all() and np.abs(y).max() < 100
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200_slice.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from distributedllm_b200 import capi
+    lib = capi.lib()
+    names = _header_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libb200slice.so does not export %s" % n
+    assert b"sm_100a" in lib.b200_version()
+
+
+def test_no_cpu_fallback():
+    """Without a B200 every entry point refuses; nothing silently routes to a CPU path."""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from distributedllm_b200 import capi\n"
+            "try:\n    capi.Slice('/nonexistent.bin')\nexcept capi.B200Error as e:\n    print('code', e.code)\n" % ROOT)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert "code 3" in out.stdout, out.stdout + out.stderr      # B200_ENODEV
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "distributedllm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+                assert "liboracle" not in src and "libllmref" not in src, fn

@@ -1,0 +1,69 @@
+"""GPU, 2 ranks: the NCCL layer-slice pipeline (b200_pipeline_*) against the un-sliced model on one GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, ctypes as C
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from distributedllm_b200 import capi, ggjt
+from distributedllm_b200.pipeline import layer_ranges
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+sh = ggjt.SHAPES["tiny128"]
+d = %(tmp)r
+a, b = layer_ranges(sh.n_layer, world)[rank]
+p = os.path.join(d, "s_%%d_%%d.bin" %% (a, b))
+if not os.path.exists(p):
+    ggjt.write_synth_slice(p, sh, a, b, ggjt.T_Q4_0, seed=0)
+sl = capi.Slice(p, local, 64)
+lib = capi.lib()
+idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    raw = np.zeros(128, np.uint8); capi.check(lib.b200_pipeline_unique_id(raw.ctypes.data)); idbuf.copy_(torch.from_numpy(raw))
+dist.broadcast(idbuf, 0)
+raw = idbuf.cpu().numpy().copy()
+capi.check(lib.b200_pipeline_init(sl.handle, rank, world, raw.ctypes.data))
+lib.b200_pipeline_result.restype = C.c_void_p; lib.b200_pipeline_result.argtypes = [C.c_void_p]
+cudart = C.CDLL("libcudart.so.12")
+rng = np.random.default_rng(21)
+ok = True
+if rank == 0:
+    whole = os.path.join(d, "whole.bin"); ggjt.write_synth_slice(whole, sh, 0, sh.n_layer - 1, ggjt.T_Q4_0, seed=0)
+    ref = capi.Slice(whole, local, 64)
+for n in (7, 1, 1, 5, 1):
+    x = rng.standard_normal((n, sh.n_embd), dtype=np.float32)
+    if rank == 0:
+        assert cudart.cudaMemcpy(C.c_void_p(sl.dev_in), C.c_void_p(x.ctypes.data), C.c_size_t(x.nbytes), 1) == 0
+    capi.check(lib.b200_pipeline_step(sl.handle, C.c_void_p(sl.dev_in), n, 1))
+    sl.sync()
+    if rank == 0:
+        out = np.empty_like(x)
+        assert cudart.cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(lib.b200_pipeline_result(sl.handle)), C.c_size_t(out.nbytes), 2) == 0
+        want = ref.forward(x)
+        ok = ok and bool((out.view(np.uint32) == want.view(np.uint32)).all())
+dist.barrier()
+capi.check(lib.b200_pipeline_destroy(sl.handle))
+if rank == 0:
+    print("PIPELINE_OK" if ok else "PIPELINE_MISMATCH")
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_nccl_pipeline_bit_exact(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "tmp": str(tmp_path)})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert "PIPELINE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
