@@ -63,6 +63,15 @@ __device__ __forceinline__ void bulk_g2s(void * dst_smem, const void * src_gmem,
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
+// 16-byte load that asks L2 to keep the line (evict_last): small, hot, read-every-token data (norm weights) must
+// survive the evict_first weight stream, otherwise every token pays an HBM round trip for it under full load
+__device__ __forceinline__ float4 ldg_keep(const float * p) {
+    uint64_t pol; float4 v;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ void grid_dep_wait()   { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -148,11 +148,23 @@ struct GemvArgs {
     int NS;                              // ring stages
     unsigned long long * trace;          // debug timeline (B200_TRACE), or null
     int pdl_early;                       // trigger dependents at kernel start instead of after the last weight copy
+    int pre_stages;                      // ring stages the producer may request before the prologue loads are issued
     int swp;                             // software-pipelined decode loop
     int dbg_nomath;                      // debug: consume ring stages without computing (streaming-rate probe)
 };
 
 __host__ __device__ inline size_t act_bytes_per_col(int nbq) { return (size_t) nbq * (128 + 16); }
+
+
+// (double) of a NON-NEGATIVE float, bit-exact, on the integer pipes: F2F.F64.F32 runs on the quarter-rate XU pipe and
+// the RMSNorm prologue needs 32 of them per thread.  Zero and subnormal inputs take the slow path.
+__device__ __forceinline__ double widen_nonneg(float f) {
+    const uint32_t u = __float_as_uint(f);
+    if (u - 0x00800000u < 0x7F000000u) return __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
+    return (double) f;
+}
+// rint() of |x| <= 2^22 through the FMA pipe (round-half-even, as F2I.RN / _mm256_round_ps(NEAREST)) instead of XU
+__device__ __forceinline__ int rint_small(float x) { return __float_as_int(fadd(x, kMagic)) - kMagicI; }
 
 // Q8_0 act-quant (ggml.c:1215-1252) of the 32 values held one per lane, written straight into the
 // dp4a word layout the matmul consumers read: words [Q][w&3][bq][w>>2], scale [b] (x dscale).
@@ -162,7 +174,7 @@ __device__ __forceinline__ void warp_quant_block(float v, int lane, int * aq_col
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
     const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
-    uint32_t pk = ((uint32_t)(__float2int_rn(fmul(v, id)) & 0xFF)) << (8 * (lane & 3));
+    uint32_t pk = ((uint32_t)(rint_small(fmul(v, id)) & 0xFF)) << (8 * (lane & 3));
     pk |= __shfl_xor_sync(0xffffffffu, pk, 1);
     pk |= __shfl_xor_sync(0xffffffffu, pk, 2);
     if ((lane & 3) == 0) {
@@ -175,9 +187,10 @@ __device__ __forceinline__ void warp_quant_block(float v, int lane, int * aq_col
 // quantise one 32-float block held in registers by ONE thread into shared memory
 template <int WT>
 __device__ __forceinline__ void thread_quant_block(const float (&v)[32], int * an, float * dn, int b) {
-    float amax = 0.f;
+    float m[8];
     #pragma unroll
-    for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
+    for (int j = 0; j < 8; j++) m[j] = fmaxf(fmaxf(fabsf(v[j]), fabsf(v[j + 8])), fmaxf(fabsf(v[j + 16]), fabsf(v[j + 24])));
+    const float amax = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
     const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
     const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
     dn[b] = (WT == kWT_Q4_0) ? fmul(d, 0.0625f) : d;        // the 1/16 of the nibble placement, folded (exact)
@@ -186,7 +199,7 @@ __device__ __forceinline__ void thread_quant_block(const float (&v)[32], int * a
     for (int w = 0; w < 8; w++) {
         uint32_t pk = 0;
         #pragma unroll
-        for (int j = 0; j < 4; j++) pk |= ((uint32_t)(__float2int_rn(fmul(v[w*4 + j], id)) & 0xFF)) << (8 * j);
+        for (int j = 0; j < 4; j++) pk |= ((uint32_t)(rint_small(fmul(v[w*4 + j], id)) & 0xFF)) << (8 * j);
         dst[(w & 3) * 8 + (w >> 2)] = (int) pk;
     }
 }
@@ -217,6 +230,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
         B200_TRACE(a.trace, 0);
         if (RING) for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWPC); }
         mbar_init(actbar, 1);
+        mbar_init(actbar + 1, kWPC);        // gate: consumers have issued their prologue loads
         mbar_fence_init();
     }
     __syncthreads();
@@ -225,10 +239,15 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
             if (a.pdl_early) grid_dep_launch();
-            int slot = 0, use = 0;
+            int slot = 0, use = 0, issued = 0;
             for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
                 const uint8_t * src = a.W.data + (long long) tile * a.W.tile_bytes;
                 for (int s = 0; s < n_stage; s++) {
+                    // Only `pre_stages` of weights may be requested before the consumers have put their (tiny, latency-
+                    // critical) prologue loads on the wire: a prologue load queued behind ~20 MB of bulk-copy requests
+                    // waits ~5 us (profiles/r01_timeline_*.txt); behind 2 stages per CTA it waits < 1 us.
+                    if (issued == a.pre_stages) mbar_wait(actbar + 1, 0);
+                    issued++;
                     if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
                     mbar_arrive_expect_tx(&full[slot], (uint32_t) stage_bytes);
                     bulk_g2s(ring + (size_t) slot * stage_bytes, src + (size_t) s * stage_bytes, (uint32_t) stage_bytes, &full[slot]);
@@ -245,11 +264,23 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
 
     // ---------------------------------------------------------------------- consumer warps
     if (!RING && tid == 0) grid_dep_launch();
+    // static data first: the norm weights do not depend on the previous kernel, so their (possibly HBM) round trip
+    // is issued before the dependency wait and kept in L2 for the next token
+    float wn[32];
+    if (PRO == PRO_NORM && nb <= kConsumers) {
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 u = tid < nb ? ldg_keep(a.norm_w + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wn[j*4] = u.x; wn[j*4+1] = u.y; wn[j*4+2] = u.z; wn[j*4+3] = u.w;
+        }
+    }
     grid_dep_wait();                                   // the input comes from the previous kernel
     if (tid == 0) B200_TRACE(a.trace, 1);
 
     const int ncols = min(NC, a.N - col0);
+    bool gate_done = false;
     if (PRO == PRO_PREQ) {
+        gate_done = true;
         // the producer of the activation already quantised it (attention / gate epilogue): two bulk copies
         if (tid == 0) {
             const uint32_t b1 = (uint32_t) ncols * nbq * 128, b2 = (uint32_t) ncols * nbq * 16;
@@ -257,6 +288,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             bulk_g2s(a_s, a.aq_in + (size_t) col0 * nbq * 32, b1, actbar);
             bulk_g2s(da_s, a.da_in + (size_t) col0 * nbq * 4, b2, actbar);
         }
+        if (RING && lane == 0) mbar_arrive(actbar + 1);
         for (int n = ncols; n < NC; n++) {
             for (int i = tid; i < nbq * 32; i += kConsumers) a_s[(size_t) n * nbq * 32 + i] = 0;
             for (int i = tid; i < nbq * 4; i += kConsumers) da_s[(size_t) n * nbq * 4 + i] = 0.f;
@@ -279,24 +311,26 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             }
             if (PRO == PRO_NORM && nb <= kConsumers) {
                 // one global round trip: x block and norm weights in flight together, x kept in registers
-                float v[32], wn[32];
+                float v[32];
                 const bool own = tid < nb;
                 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const float4 t = own ? *(const float4 *)(x + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 u = own ? *(const float4 *)(a.norm_w + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
-                    wn[j*4] = u.x; wn[j*4+1] = u.y; wn[j*4+2] = u.z; wn[j*4+3] = u.w;
                 }
-                double s = 0.0;
+                if (RING && n == ncols - 1 && lane == 0) { gate_done = true; mbar_arrive(actbar + 1); }
+                double s4[4] = {0.0, 0.0, 0.0, 0.0};
                 #pragma unroll
-                for (int j = 0; j < 32; j++) s += (double) fmul(v[j], v[j]);
+                for (int j = 0; j < 32; j++) s4[j & 3] += widen_nonneg(fmul(v[j], v[j]));
+                double s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                if (tid == 0) B200_TRACE(a.trace, 5);
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane == 0) red[warp] = s;
                 named_bar_sync(1, kConsumers);
                 const double tot = (red[0] + red[1]) + (red[2] + red[3]);
                 named_bar_sync(1, kConsumers);
                 const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) K), 1e-6f)));
+                if (tid == 0) B200_TRACE(a.trace, 6);
                 if (own) {
                     #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmul(fmul(v[j], scale), wn[j]);
@@ -335,6 +369,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             }
         }
     }
+    if (RING && lane == 0 && !gate_done) mbar_arrive(actbar + 1);     // slow-path prologues open the gate late
     named_bar_sync(1, kConsumers);
     if (tid == 0) B200_TRACE(a.trace, 2);
 
@@ -348,6 +383,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             for (int n = 0; n < NC; n++) { acc[g][n][0] = 0.f; acc[g][n][1] = 0.f; }
         const uint8_t * gsrc = a.W.data + (long long) tile * a.W.tile_bytes;
 
+#ifdef B200_ENABLE_SWP   // experiment kept for reference: exact, but slower and 160 registers (2 CTAs/SM); see DESIGN.md
         if (NC == 1 && !a.dbg_nomath && a.swp) {
             // ---- decode path: software-pipelined over units of PQ quads.  Unit u+1's shared-memory loads
             // (weights, scales, activation words) are issued into a second register set BEFORE unit u is
@@ -424,6 +460,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 }
             }
         } else
+#endif
         for (int s = 0; s < n_stage; s++) {
             const uint8_t * base;
             if (RING) {
@@ -580,7 +617,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                         for (int w8 = 0; w8 < 8; w8++) {
                             uint32_t pk = 0;
                             #pragma unroll
-                            for (int j = 0; j < 4; j++) pk |= ((uint32_t)(__float2int_rn(fmul(v[w8*4 + j], id)) & 0xFF)) << (8 * j);
+                            for (int j = 0; j < 4; j++) pk |= ((uint32_t)(rint_small(fmul(v[w8*4 + j], id)) & 0xFF)) << (8 * j);
                             dst[(w8 & 3) * 8 + (w8 >> 2)] = (int) pk;
                         }
                     }
@@ -621,7 +658,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                     for (int w8 = 0; w8 < 8; w8++) {
                         uint32_t pk = 0;
                         #pragma unroll
-                        for (int j = 0; j < 4; j++) pk |= ((uint32_t)(__float2int_rn(fmul(v[w8*4 + j], id)) & 0xFF)) << (8 * j);
+                        for (int j = 0; j < 4; j++) pk |= ((uint32_t)(rint_small(fmul(v[w8*4 + j], id)) & 0xFF)) << (8 * j);
                         dst[(w8 & 3) * 8 + (w8 >> 2)] = (int) pk;
                     }
                 }
@@ -942,6 +979,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     }
     __syncthreads();
 
+    if (threadIdx.x == 0) B200_TRACE(a.trace, 2);
     float * scg = a.sc_scratch + ((size_t) ny * a.H + h) * a.n_ctx;
     // ---- phase 1: scores of the positions this CTA owns
     {
@@ -983,7 +1021,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) B200_TRACE(a.trace, 4);
     cluster_sync_all();
+    if (threadIdx.x == 0) B200_TRACE(a.trace, 5);
 
     // ---- phase 2: softmax over all t < tcount (every CTA, identical results)
     float mx = -INFINITY;
@@ -1009,6 +1049,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     for (int t = tid; t < tcount; t += 256) p16[t] = f2h(fmul(sc[t], inv));
     __syncthreads();
 
+    if (threadIdx.x == 0) B200_TRACE(a.trace, 6);
     // ---- phase 3: V.p partial sums of slots 8g..8g+7
     const int npT = T & ~31, lim = min(npT, tcount);
     float * partg = a.part_scratch + (((size_t) ny * a.H + h) * 4) * 1024;
@@ -1032,6 +1073,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     }
     __syncthreads();
     cluster_sync_all();
+    if (threadIdx.x == 0) B200_TRACE(a.trace, 7);
 
     // ---- phase 4: CTA g finishes channels [32g, 32g+32)
     if (tid < 32) {

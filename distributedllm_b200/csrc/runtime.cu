@@ -100,16 +100,29 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
     static bool attr_set[16] = {false};
     const size_t stage = (size_t) kQS * TR * CB;
     const size_t act = (size_t) NC * act_bytes_per_col(a.W.nbq) + 34 * 8 + kWPC * 8 + (size_t) NC * 128 + 64;
-    int NS = RING ? (s->opt_ns > 0 ? s->opt_ns : 8 / G) : 0;
-    while (NS > 2 && NS * stage + act > (size_t) kSmemLimit) NS--;
-    if (NS > 16) NS = 16;
+    // Ring depth: as deep as possible while EVERY tile of the matrix still gets a co-resident CTA (no second wave):
+    // wide matrices (qkv 384 tiles, w1|w3 688) run 3-5 small-ring CTAs per SM, narrow ones (wo, w2: 128 tiles) one
+    // CTA per SM with a deep ring.  B200_NS overrides.
+    int NS = 0;
+    if (RING) {
+        const int ncolg = (a.N + NC - 1) / NC;
+        int need = (a.W.n_tiles * ncolg + s->n_sm - 1) / s->n_sm;
+        if (need > 5) need = 5;
+        const size_t budget = (size_t) kSmemLimit / need - 1024;
+        NS = s->opt_ns > 0 ? s->opt_ns : (budget > act ? (int)((budget - act) / stage) : 2);
+        if (NS < 2) NS = 2;
+        if (NS > 16) NS = 16;
+        while (NS > 2 && NS * stage + act > (size_t) kSmemLimit) NS--;
+    }
     const size_t smem = NS * stage + act;
     if (smem > (size_t) kSmemLimit) return fail(B200_EINVAL, "gemv needs %zu B of shared memory (K=%d, NC=%d)", smem, a.W.K, NC);
     if (!attr_set[s->device & 15]) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        // without this the driver's carve-out heuristic leaves room for only 2 CTAs/SM however small the ring is
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[s->device & 15] = true;
     }
-    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pdl_early = env_int("B200_PDL_EARLY", 0); a.swp = env_int("B200_SWP", 0);
+    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pdl_early = env_int("B200_PDL_EARLY", 0); a.swp = env_int("B200_SWP", 0); a.pre_stages = env_int("B200_PRE", 2);
     a.trace = nullptr;
     if (s->trace && s->trace_next < 512) { a.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(s->cur_class); }
     int per_sm = s->opt_cta_per_sm > 0 ? s->opt_cta_per_sm : (int)(kSmemLimit / (smem + 1024));

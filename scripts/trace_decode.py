@@ -29,4 +29,18 @@ for i in range(first, n):
     if t_base is None: t_base = d[:, 0].min()
     f = lambda col, fn: (fn(d[:, col][d[:, col] > 0]) - t_base) / 1e3 if (d[:, col] > 0).any() else float("nan")
     print("%3d %6s %5d | %8.2f %8.2f | %8.2f | %8.2f | %8.2f | %8.2f" % (i - first, names[cls[i]], k, f(0, np.min), f(0, np.max), f(1, np.min), f(2, np.max), f(4, np.max), f(3, np.max)))
+print("\nper-CTA durations [us]: prologue = t2-t1, main = t3-t2 (min / median / p90 / max)")
+for i in range(first, min(n, first + 5)):
+    k = ctas[i]; d = buf[i, :k].astype(np.int64)
+    if (d[:, 2] > 0).any():
+        pro = (d[:, 2] - d[:, 1]) / 1e3; main = (d[:, 3] - d[:, 2]) / 1e3
+        q = lambda a: "%.2f / %.2f / %.2f / %.2f" % (a.min(), np.median(a), np.percentile(a, 90), a.max())
+        print("%6s prologue %s | main %s | t1 spread %.2f" % (names[cls[i]], q(pro), q(main), (d[:, 1].max() - d[:, 1].min()) / 1e3))
+        if (d[:, 5] > 0).any():
+            print("        prologue split: load+sum %s | reduce+scale %s | quant+bar %s" % (q((d[:, 5] - d[:, 1]) / 1e3), q((d[:, 6] - d[:, 5]) / 1e3), q((d[:, 2] - d[:, 6]) / 1e3)))
+    else:
+        tot = (d[:, 3] - d[:, 1]) / 1e3
+        print("%6s total %.2f / %.2f / %.2f" % (names[cls[i]], tot.min(), np.median(tot), tot.max()))
+        m = lambda a_, b_: np.median((d[:, a_] - d[:, b_]) / 1e3)
+        print("        median phases: rope/q %.2f | scores %.2f | cluster sync %.2f | softmax %.2f | V.p+sync %.2f | finish %.2f" % (m(2, 1), m(4, 2), m(5, 4), m(6, 5), m(7, 6), m(3, 7)))
 sl.close()
