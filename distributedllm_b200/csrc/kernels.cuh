@@ -141,7 +141,7 @@ struct GemvArgs {
     const float * resid;  int ldr;       // EPI_RESID
     float * y;            int ldy;       // output [N][ldy]
     int * aq_out; float * da_out; int out_nbq; float out_dscale;   // EPI_GATEQ / EPI_RESID_NQ: quantised output for the next matmul
-    const float * nq_norm_w; int * nq_counter;   // EPI_RESID_NQ: next RMSNorm weight [out_rows]; one ticket counter per column group
+    const float * nq_norm_w; int * nq_counter; double * nq_partial;   // EPI_RESID_NQ: next RMSNorm weight [out_rows]; 2 counters per column group; per-tile sums of squares
     int N;                               // columns (tokens)
     int out_rows;                        // valid output rows (E, 3E, or FF for the gate)
     const uint16_t * tsilu;              // EPI_GATE*: fp16 SiLU table (65536 entries)
@@ -557,6 +557,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                             float v = res[g][n];
                             if (EPI == EPI_RESID || EPI == EPI_RESID_NQ) v = fadd(v, a.resid[(size_t)(col0 + n) * a.ldr + row]);
                             a.y[(size_t)(col0 + n) * a.ldy + row] = v;
+                            if (EPI == EPI_RESID_NQ) gq[n * 32 + warp * 8 + r] = v;
                         }
                     }
                 }
@@ -564,104 +565,47 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
         }
     }
     if (EPI == EPI_RESID_NQ) {
-        // The output vector feeds an RMSNorm + weight matmul next.  The LAST CTA of this column group to finish
-        // (ticket counter) normalises and Q8_0-quantises the whole row(s) once, so the next kernel starts from a
-        // 4.6 KB bulk copy instead of every one of its CTAs re-reading and re-normalising x behind the weight stream.
-        __shared__ int is_last;
-        __threadfence();
+        // The output row feeds an RMSNorm + weight matmul next.  Instead of every CTA of that matmul re-reading and
+        // re-normalising the whole row (16 KB of LDGs that queue behind its own weight stream: ~3 us per kernel, and
+        // 20 % extra L2 traffic), THIS kernel finishes the job while the values are still on chip:
+        //   every CTA owns exactly one 32-row tile = one Q8_0 block (the host guarantees gridDim.x == n_tiles);
+        //   1. partial sum of squares of its block -> global;  2. grid-wide arrive + spin on a counter;
+        //   3. every CTA adds the n_tiles partials in the same fixed order -> identical RMS scale everywhere;
+        //   4. normalise, multiply by the norm weight, Q8_0-quantise its own block into the consumer's word layout.
+        // All CTAs are co-resident (grid <= SM count x CTAs/SM, and dependents are launched only after every CTA of
+        // this grid has started), so the spin cannot deadlock.
         named_bar_sync(1, kConsumers);
-        if (tid == 0) {
-            const int ticket = atomicAdd(a.nq_counter + blockIdx.y, 1);
-            is_last = ticket == (int) gridDim.x - 1;
-            if (is_last) a.nq_counter[blockIdx.y] = 0;
-        }
-        named_bar_sync(1, kConsumers);
-        if (is_last) {
-            __threadfence();
-            const int Ko = a.out_rows, nbo = Ko / 32;
+        if (warp == 0) {
+            const int tile = blockIdx.x, nt = (int) gridDim.x;
             for (int n = 0; n < ncols; n++) {
-                const float * yrow = a.y + (size_t)(col0 + n) * a.ldy;
-                int * aq = a.aq_out + (size_t)(col0 + n) * a.out_nbq * 32;
-                float * dq = a.da_out + (size_t)(col0 + n) * a.out_nbq * 4;
-                if (nbo <= kConsumers) {
-                    // one L2 round trip: the row and the norm weights in flight together, row kept in registers
-                    float v[32], wn[32];
-                    const bool own = tid < nbo;
-                    #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 t = own ? __ldcg((const float4 *)(yrow + tid * 32 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 u = own ? *(const float4 *)(a.nq_norm_w + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
-                        wn[j*4] = u.x; wn[j*4+1] = u.y; wn[j*4+2] = u.z; wn[j*4+3] = u.w;
-                    }
-                    double s = 0.0;
-                    #pragma unroll
-                    for (int j = 0; j < 32; j++) s += (double) fmul(v[j], v[j]);
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) red[warp] = s;
-                    named_bar_sync(1, kConsumers);
-                    const double tot = (red[0] + red[1]) + (red[2] + red[3]);
-                    named_bar_sync(1, kConsumers);
-                    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) Ko), 1e-6f)));
-                    if (own) {
-                        #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] = fmul(fmul(v[j], scale), wn[j]);
-                        float amax = 0.f;
-                        #pragma unroll
-                        for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
-                        const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
-                        const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
-                        dq[tid] = fmul(d, a.out_dscale);
-                        int * dst = aq + (tid >> 2) * 32 + (tid & 3) * 2;
-                        #pragma unroll
-                        for (int w8 = 0; w8 < 8; w8++) {
-                            uint32_t pk = 0;
-                            #pragma unroll
-                            for (int j = 0; j < 4; j++) pk |= ((uint32_t)(rint_small(fmul(v[w8*4 + j], id)) & 0xFF)) << (8 * j);
-                            dst[(w8 & 3) * 8 + (w8 >> 2)] = (int) pk;
-                        }
-                    }
-                    continue;
-                }
-                double s = 0.0;
-                for (int b = tid; b < nbo; b += kConsumers) {
-                    #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 v = __ldcg((const float4 *)(yrow + b * 32 + j * 4));
-                        s += (double) fmul(v.x, v.x); s += (double) fmul(v.y, v.y);
-                        s += (double) fmul(v.z, v.z); s += (double) fmul(v.w, v.w);
-                    }
-                }
+                const float val = gq[n * 32 + lane];
+                double s = widen_nonneg(fmul(val, val));
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) red[warp] = s;
-                named_bar_sync(1, kConsumers);
-                const double tot = (red[0] + red[1]) + (red[2] + red[3]);
-                named_bar_sync(1, kConsumers);
-                const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) Ko), 1e-6f)));
-                for (int b = tid; b < nbo; b += kConsumers) {
-                    float v[32];
-                    #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 t = __ldcg((const float4 *)(yrow + b * 32 + j * 4));
-                        const float4 wv = *(const float4 *)(a.nq_norm_w + b * 32 + j * 4);
-                        v[j*4] = fmul(fmul(t.x, scale), wv.x); v[j*4+1] = fmul(fmul(t.y, scale), wv.y);
-                        v[j*4+2] = fmul(fmul(t.z, scale), wv.z); v[j*4+3] = fmul(fmul(t.w, scale), wv.w);
-                    }
-                    float amax = 0.f;
-                    #pragma unroll
-                    for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
-                    const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
-                    const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
-                    dq[b] = fmul(d, a.out_dscale);
-                    int * dst = aq + (b >> 2) * 32 + (b & 3) * 2;
-                    #pragma unroll
-                    for (int w8 = 0; w8 < 8; w8++) {
-                        uint32_t pk = 0;
-                        #pragma unroll
-                        for (int j = 0; j < 4; j++) pk |= ((uint32_t)(rint_small(fmul(v[w8*4 + j], id)) & 0xFF)) << (8 * j);
-                        dst[(w8 & 3) * 8 + (w8 >> 2)] = (int) pk;
-                    }
-                }
+                double * part = a.nq_partial + ((size_t) blockIdx.y * NC + n) * nt;
+                if (lane == 0) part[tile] = s;
+            }
+            int * cnt = a.nq_counter + 2 * blockIdx.y;
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(cnt, 1);
+                while (*(volatile int *) cnt < nt) { }
+                __threadfence();
+            }
+            __syncwarp();
+            const int row = tile * 32 + lane;
+            for (int n = 0; n < ncols; n++) {
+                const double * part = a.nq_partial + ((size_t) blockIdx.y * NC + n) * nt;
+                double s = 0.0;
+                for (int i = lane; i < nt; i += 32) s += __ldcg(part + i);
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(s / (double) a.out_rows), 1e-6f)));
+                const float val = gq[n * 32 + lane];
+                const float wv = row < a.out_rows ? a.nq_norm_w[row] : 0.f;
+                warp_quant_block(fmul(fmul(val, scale), wv), lane, a.aq_out + (size_t)(col0 + n) * a.out_nbq * 32,
+                                 a.da_out + (size_t)(col0 + n) * a.out_nbq * 4, tile, a.out_dscale);
+            }
+            if (lane == 0) {                                   // the last CTA through re-arms the counters
+                if (atomicAdd(cnt + 1, 1) == nt - 1) { cnt[0] = 0; cnt[1] = 0; }
             }
         }
     }
