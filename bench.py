@@ -41,6 +41,9 @@ N_CTX = 512
 PREFILL = 256
 SEED = 0
 FALLBACK_HBM_GBS = 6650.0
+# dram__bytes_read.sum + dram__bytes_write.sum per k_gemv launch, averaged over the 4 launches of a layer, from the
+# ncu --set full capture committed under profiles/ (None until that capture exists for the current kernels)
+NCU_TRAFFIC_PER_LAUNCH = 29.05e6    # profiles/r01_decode_kernels_ncu_full.md: (28.4 + 9.47 + 52.3 + 26.0) MB per layer / 4 launches; algorithmic 28.47e6
 
 
 def model_dir() -> str:
@@ -351,14 +354,41 @@ def run_b200(args):
         peak, peak_src = measured_peak()
         wbytes = float(info.weight_bytes)                       # this rank's slice, bytes as stored in the file
         achieved = wbytes * nprof / (gemv_ms / 1e3) / 1e9
+        # the same kernels INSIDE the replayed graph (PDL overlap and all), from in-kernel %globaltimer stamps:
+        # duration of a launch = last CTA exit - first CTA entry
+        in_graph = None
+        try:
+            sl.trace_enable(True)
+            nlayer = info.n_layer
+            for i in range(3):
+                sl.forward_device(sl.dev_in, 1, sl.dev_out)
+            stamps, cls, ctas = sl.trace_read()
+            sl.trace_enable(False)
+            per = 5 * nlayer
+            dur = {}
+            for j in range(len(cls) - per, len(cls)):
+                d = stamps[j, :ctas[j]].astype(np.int64)
+                dur.setdefault(int(cls[j]), []).append((d[:, 3].max() - d[:, 0].min()) / 1e3)
+            g_us = sum(sum(dur.get(c, [])) for c in (0, 3, 4, 5))
+            first = stamps[len(cls) - per, :ctas[len(cls) - per]].astype(np.int64)[:, 0].min()
+            last = stamps[len(cls) - 1, :ctas[len(cls) - 1]].astype(np.int64)[:, 3].max()
+            in_graph = {"gemv_us_per_token": g_us, "achieved": wbytes / (g_us * 1e-6) / 1e9, "frac": wbytes / (g_us * 1e-6) / 1e9 / peak,
+                        "step_us_first_entry_to_last_exit": (last - first) / 1e3,
+                        "per_class_us_per_token": {nm: float(sum(dur.get(c, []))) for c, nm in
+                                                   ((0, "qkv"), (2, "attention"), (3, "wo"), (4, "w13"), (5, "w2"))},
+                        "note": "launches overlap under programmatic dependent launch, so per-class times can sum to more than the step"}
+        except Exception as ex:
+            in_graph = {"error": repr(ex)}
         roof = {"bound": "hbm", "kernel": "k_gemv (Q4_0xQ8_0 exact-mode weight matmul; qkv, wo, w1|w3, w2 = 4 launches/layer)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": None,
+                "traffic": NCU_TRAFFIC_PER_LAUNCH,
+                "timing": "CUDA events bracketing every launch, un-graphed (adds ~4 us of event overhead per launch; see in_graph)",
                 "algorithmic_bytes_per_launch": wbytes * nprof / max(1, gemv_launches),
                 "avg_launch_us": 1e3 * gemv_ms / max(1, gemv_launches),
                 "share_of_step": gemv_ms / float(ms.sum()),
                 "per_class_us_per_token": {n: 1e3 * float(m) / nprof for n, m in
-                                           zip(("qkv", "rope_append", "attention", "wo", "w13", "w2", "advance"), ms)}}
+                                           zip(("qkv", "rope_append", "attention", "wo", "w13", "w2", "advance"), ms)},
+                "in_graph": in_graph}
     # whole-step roofline: B(p) = W + KV read + KV write, mean over the positions of the timed steps
     W_all = 32 * (4 * (E * E // 32 * 18) + 3 * (E * sh.n_ff // 32 * 18)) + 32 * 2 * E * 4
     kv_pos = 32 * 2 * E * 2

@@ -57,6 +57,8 @@ def lib() -> C.CDLL:
         L.b200_slice_profile.argtypes = [vp, ci]
         L.b200_slice_profile_read.argtypes = [vp, vp, vp, ci]
         L.b200_debug_read.argtypes = [vp, ci, C.c_size_t, C.c_size_t, vp]
+        L.b200_debug_trace_enable.argtypes = [vp, ci]
+        L.b200_debug_trace_read.argtypes = [vp, vp, vp, vp, ci]
         L.b200_slice_dev_in.argtypes = [vp]
         L.b200_slice_dev_in.restype = vp
         L.b200_slice_dev_out.argtypes = [vp]
@@ -157,6 +159,17 @@ class Slice:
         out = np.zeros(count, np.uint32)
         check(lib().b200_debug_read(self._h, which, 0, count, _ptr(out)))
         return out.view(dtype)
+
+    def trace_enable(self, on: bool) -> None:
+        check(lib().b200_debug_trace_enable(self._h, int(on)))
+
+    def trace_read(self, max_launches: int = 512):
+        """-> (stamps [n][ctas][8] uint64 ns, class ids [n], cta counts [n])"""
+        buf = np.zeros((max_launches, 1024, 8), np.uint64)
+        cls = np.zeros(max_launches, np.int32)
+        ctas = np.zeros(max_launches, np.int32)
+        n = lib().b200_debug_trace_read(self._h, _ptr(buf), _ptr(cls), _ptr(ctas), max_launches)
+        return buf[:n], cls[:n], ctas[:n]
 
     def last_ms(self) -> float:
         return float(lib().b200_slice_last_ms(self._h))

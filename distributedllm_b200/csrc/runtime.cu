@@ -715,6 +715,26 @@ int b200_slice_profile_read(b200_slice_t * s, float * ms_by_class, int * launche
     return 0;
 }
 
+/* Switch the in-kernel timeline on or off at run time (drops the captured decode graphs so the next step re-captures). */
+int b200_debug_trace_enable(b200_slice_t * s, int on) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    for (auto & kv : s->graphs) cudaGraphExecDestroy(kv.second);
+    s->graphs.clear();
+    static unsigned long long * parked = nullptr;
+    if (on) {
+        if (!s->trace) {
+            if (parked) { s->trace = parked; parked = nullptr; }
+            else { int rc = dev_alloc(s, &s->trace, (size_t) 512 * 1024 * 8); if (rc) return rc; }
+        }
+        B200_CUDA(cudaMemset(s->trace, 0, (size_t) 512 * 1024 * 8 * 8));
+        s->trace_next = 0; s->trace_cls.clear(); s->trace_ctas.clear();
+    } else if (s->trace) { parked = s->trace; s->trace = nullptr; }
+    return 0;
+}
+
 /* Debug timeline: when B200_TRACE=1 every matmul / attention launch of the NEXT captured graph (or un-graphed step)
  * stamps %globaltimer per CTA: [0] entry, [1] after griddepcontrol.wait, [2] prologue done, [3] exit, [4] last weight copy issued. */
 int b200_debug_trace_read(b200_slice_t * s, unsigned long long * out, int * cls, int * ctas, int max_launches) {
