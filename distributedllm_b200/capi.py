@@ -51,6 +51,7 @@ def lib() -> C.CDLL:
         L.b200_slice_last_ms.restype = cf
         L.b200_slice_launch_count.argtypes = [vp]
         L.b200_slice_launch_count.restype = C.c_int64
+        L.b200_slice_set_fast_prefill.argtypes = [vp, ci, ci]
         L.b200_slice_mark.argtypes = [vp, ci]
         L.b200_slice_mark_elapsed_ms.argtypes = [vp]
         L.b200_slice_mark_elapsed_ms.restype = cf
@@ -139,6 +140,9 @@ class Slice:
     @property
     def dev_out(self) -> int:
         return lib().b200_slice_dev_out(self._h)
+
+    def set_fast_prefill(self, on: bool, min_tokens: int = 0) -> None:
+        check(lib().b200_slice_set_fast_prefill(self._h, int(on), min_tokens))
 
     def mark(self, which: int) -> None:
         check(lib().b200_slice_mark(self._h, which))

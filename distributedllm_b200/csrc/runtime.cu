@@ -5,6 +5,7 @@
 // one B200.  One stream per slice; the N=1 decode step is a CUDA graph replayed per token with
 // the position kept in device memory.
 #include "kernels.cuh"
+#include "fastgemm.cuh"
 #include "ggjt_file.hpp"
 
 #include <cmath>
@@ -53,6 +54,7 @@ struct b200_slice {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
     int64_t launches = 0, weight_bytes = 0;
     bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true;
+    bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
     int opt_ns = 0, opt_qs = 0, opt_cta_per_sm = 0;
     std::mutex mu;
     // per-kernel-class event timing (b200_slice_profile): class 0 qkv, 1 rope, 2 attention, 3 wo, 4 w13, 5 w2, 6 advance
@@ -191,6 +193,26 @@ static int launch_f16(b200_slice * s, GemvF16Args a) {
     return launch_simple(s, kern, dim3(gx, a.N, 1), dim3(256, 1, 1), smem, a);
 }
 
+// ---------------------------------------------------------------- fast-mode prefill (tcgen05), see fastgemm.cuh
+template <bool NORM>
+static int launch_prep(b200_slice * s, const float * x, int ldx, const float * norm_w, int K, int N) {
+    PrepArgs p{x, ldx, norm_w, s->xh, K, N};
+    return launch_simple(s, k_prep_q8_f16<NORM>, dim3(N, 1, 1), dim3(256, 1, 1), 0, p);
+}
+template <int EPI>
+static int launch_fast_gemm(b200_slice * s, const PackedW & W, const float * resid, int ldr, float * y, int ldy, int N, int out_rows) {
+    static bool attr_set[16] = {false};
+    auto kern = k_gemm_q4_tc<EPI>;
+    if (!attr_set[s->device & 15]) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFgSmem));
+        attr_set[s->device & 15] = true;
+    }
+    FastGemmArgs a{}; a.W = W; a.xh = s->xh; a.resid = resid; a.ldr = ldr; a.y = y; a.ldy = ldy; a.N = N; a.out_rows = out_rows;
+    a.tsilu = s->tsilu;
+    const int groups = W.n_tiles * W.TR;                     // 8-row groups in packed order
+    return launch_simple(s, kern, dim3((groups + 15) / 16, (N + kFgN - 1) / kFgN, 1), dim3(160, 1, 1), kFgSmem, a);
+}
+
 // ---------------------------------------------------------------- one forward over the slice
 // Enqueue every layer for N tokens at device-side position *d_npast (tensor_processor.cpp:537-766).
 static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) {
@@ -199,6 +221,8 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
     for (int il = 0; il < s->L; il++) {
         LayerW & Lw = s->layers[il];
         // grid-barrier norm+quant epilogue: decode only (every CTA of wo / w2 must be co-resident: 1 tile per CTA)
+        const bool fast = s->fast_prefill && N >= s->fast_min_tokens && s->wtype == kWT_Q4_0 && (Lw.qkv.n_tiles * Lw.qkv.TR) % 16 == 0 &&
+                          (Lw.wo.n_tiles * Lw.wo.TR) % 16 == 0 && (Lw.w13.n_tiles * Lw.w13.TR) % 16 == 0;
         const bool nq = s->use_nq && N == 1 && s->wtype != kWT_F16 && Lw.wo.n_tiles <= 256 && Lw.wo.n_tiles <= s->n_sm * 2;
         float * nxt = (il == s->L - 1) ? out : ((il & 1) ? s->xb : s->xa);
         uint16_t * kc = s->kc + (size_t) il * s->n_ctx * E, * vc = s->vc + (size_t) il * s->n_ctx * E;
@@ -210,6 +234,9 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             f.W = Lw.f_q; f.y = s->qkv;         if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
             f.W = Lw.f_k; f.y = s->qkv + E;     if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
             f.W = Lw.f_v; f.y = s->qkv + 2 * E; if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
+        } else if (fast) {
+            if ((rc = launch_prep<true>(s, cur, E, Lw.attn_norm, E, N))) return rc;
+            if ((rc = launch_fast_gemm<FG_STORE>(s, Lw.qkv, nullptr, 0, s->qkv, 3 * E, N, 3 * E))) return rc;
         } else {
             GemvArgs g{}; g.W = Lw.qkv; g.x = cur; g.ldx = E; g.norm_w = Lw.attn_norm; g.y = s->qkv; g.ldy = 3 * E;
             g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x;
@@ -266,6 +293,16 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             GemvF16Args w{}; w.K = FF; w.x = s->gate; w.ldx = FF; w.N = N; w.tsilu = s->tsilu;
             w.rows = E; w.W = Lw.f_2; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
             if ((rc = launch_f16<PRO_PLAIN, EPI_RESID>(s, w))) return rc;
+        } else if (fast) {
+            s->cur_class = 3;
+            if ((rc = launch_prep<false>(s, s->att, E, nullptr, E, N))) return rc;
+            if ((rc = launch_fast_gemm<FG_RESID>(s, Lw.wo, cur, E, s->ffin, E, N, E))) return rc;
+            s->cur_class = 4;
+            if ((rc = launch_prep<true>(s, s->ffin, E, Lw.ffn_norm, E, N))) return rc;
+            if ((rc = launch_fast_gemm<FG_GATE>(s, Lw.w13, nullptr, 0, s->gate, FF, N, FF))) return rc;
+            s->cur_class = 5;
+            if ((rc = launch_prep<false>(s, s->gate, FF, nullptr, FF, N))) return rc;
+            if ((rc = launch_fast_gemm<FG_RESID>(s, Lw.w2, s->ffin, E, nxt, E, N, E))) return rc;
         } else {
             const float dsc = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
             s->cur_class = 3;
@@ -524,6 +561,7 @@ static int load_locked(b200_slice * s, const char * path) {
         (rc = dev_alloc(s, &s->d_out, nE)) || (rc = dev_alloc(s, &s->d_npast, 1)) ||
         (rc = dev_alloc(s, &s->sc_scratch, (size_t) 32 * s->H * s->n_ctx)) || (rc = dev_alloc(s, &s->part_scratch, (size_t) 32 * s->H * 4096)))
         return rc;
+    if ((rc = dev_alloc(s, &s->xh, (size_t) s->n_ctx * (FF > E ? FF : E) + 64))) return rc;
     if (s->wtype != kWT_F16) {
         s->nbqE = s->layers[0].wo.nbq; s->nbqF = s->layers[0].w2.nbq;
         const size_t nq = (size_t) s->n_ctx;
@@ -595,6 +633,7 @@ int b200_slice_load(const char * path, int device, int n_ctx, b200_slice_t ** ou
     s->use_ring  = env_int("B200_RING", 1) != 0;
     s->use_graph = env_int("B200_GRAPH", 1) != 0;
     s->use_pdl   = env_int("B200_PDL", 1) != 0;
+    s->fast_prefill = env_int("B200_FAST_PREFILL", 0) != 0; s->fast_min_tokens = env_int("B200_FAST_MIN_TOKENS", 32);
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
     s->opt_ns = env_int("B200_NS", 0); s->opt_qs = env_int("B200_QS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0);
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -674,6 +713,14 @@ float b200_slice_last_ms(b200_slice_t * s) {
 int64_t b200_slice_launch_count(b200_slice_t * s) { return s ? s->launches : 0; }
 float * b200_slice_dev_in(b200_slice_t * s)  { return s ? s->d_in : nullptr; }
 float * b200_slice_dev_out(b200_slice_t * s) { return s ? s->d_out : nullptr; }
+
+int b200_slice_set_fast_prefill(b200_slice_t * s, int on, int min_tokens) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->fast_prefill = on != 0;
+    if (min_tokens > 0) s->fast_min_tokens = min_tokens;
+    return 0;
+}
 
 int b200_slice_mark(b200_slice_t * s, int which) {
     if (!s || which < 0 || which > 1) return fail(B200_EINVAL, "bad argument");

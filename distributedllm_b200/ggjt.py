@@ -322,6 +322,7 @@ SHAPES = {
     "tiny":   ModelShape(512, 256, 32, 4, 4),        # d_head 64, n_ff 704
     "tiny3b": ModelShape(512, 800, 32, 8, 3),        # d_head 100 (OpenLLaMA-3B-like head), n_ff 2144 = 67 blocks
     "tiny128": ModelShape(512, 512, 32, 4, 3),       # d_head 128 (the 7B/13B head size), n_ff 1376 = 43 blocks
+    "tiny128b": ModelShape(512, 512, 64, 4, 2),      # d_head 128, n_ff 1408: every matrix is a whole number of 128-row MMA tiles
     "3b":     ModelShape(32000, 3200, 216, 32, 26),  # OpenLLaMA-3B: n_ff 8640
     "7b":     ModelShape(32000, 4096, 256, 32, 32),
     "13b":    ModelShape(32000, 5120, 256, 40, 40),

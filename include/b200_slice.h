@@ -75,6 +75,12 @@ int b200_slice_forward(b200_slice_t * s, const float * in, int n_tokens, float *
  * `sync` != 0.  Used when the activation already lives in HBM (chained slices, benchmarks). */
 int b200_slice_forward_device(b200_slice_t * s, const float * d_in, int n_tokens, float * d_out, int sync);
 
+/* Fast mode for prefill calls (n_tokens >= min_tokens): the Q4_0 weight matmuls run on the tcgen05 tensor cores with
+ * the dequantisation fused in (csrc/fastgemm.cuh).  NOT bit-exact: operands are rounded to fp16 after the reference's
+ * Q8_0 activation quantisation; deviation from exact mode is bounded in tests/test_gpu_fast_prefill.py.  Off by default
+ * (or B200_FAST_PREFILL=1); decode steps always run in exact mode. */
+int b200_slice_set_fast_prefill(b200_slice_t * s, int on, int min_tokens);
+
 /* Block until everything queued on the slice's stream has finished. */
 int b200_slice_sync(b200_slice_t * s);
 
