@@ -185,8 +185,9 @@ __device__ __forceinline__ void warp_quant_block(float v, int lane, int * aq_col
 }
 
 // quantise one 32-float block held in registers by ONE thread into shared memory
+// `rot`: v[4*w8 .. 4*w8+3] holds 16-byte chunk (w8 + rot) & 7 of the block (bank-conflict-free rotated smem reads)
 template <int WT>
-__device__ __forceinline__ void thread_quant_block(const float (&v)[32], int * an, float * dn, int b) {
+__device__ __forceinline__ void thread_quant_block(const float (&v)[32], int * an, float * dn, int b, int rot = 0) {
     float m[8];
     #pragma unroll
     for (int j = 0; j < 8; j++) m[j] = fmaxf(fmaxf(fabsf(v[j]), fabsf(v[j + 8])), fmaxf(fabsf(v[j + 16]), fabsf(v[j + 24])));
@@ -200,7 +201,8 @@ __device__ __forceinline__ void thread_quant_block(const float (&v)[32], int * a
         uint32_t pk = 0;
         #pragma unroll
         for (int j = 0; j < 4; j++) pk |= ((uint32_t)(rint_small(fmul(v[w*4 + j], id)) & 0xFF)) << (8 * j);
-        dst[(w & 3) * 8 + (w >> 2)] = (int) pk;
+        const int ww = (w + rot) & 7;
+        dst[(ww & 3) * 8 + (ww >> 2)] = (int) pk;
     }
 }
 
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
     uint64_t * actbar = empty + 16;
     double * red = (double *)(actbar + 2);           // [kWPC]
     float * gq = (float *)(red + kWPC);              // [NC][32] gate values of one tile (EPI_GATEQ)
+    float * xs = gq + NC * 32;                       // [K] input row staged by one bulk copy (PRO_NORM, NC == 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int col0 = blockIdx.y * NC;
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
     if (PRO == PRO_NORM && nb <= kConsumers) {
         #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const float4 u = tid < nb ? ldg_keep(a.norm_w + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 u = tid < nb ? ldg_keep(a.norm_w + tid * 32 + (((NC == 1 ? tid : 0) + j) & 7) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             wn[j*4] = u.x; wn[j*4+1] = u.y; wn[j*4+2] = u.z; wn[j*4+3] = u.w;
         }
     }
@@ -313,12 +316,28 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 // one global round trip: x block and norm weights in flight together, x kept in registers
                 float v[32];
                 const bool own = tid < nb;
-                #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 t = own ? *(const float4 *)(x + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
+                const int rot = NC == 1 ? (tid & 7) : 0;
+                if (NC == 1) {
+                    // one TMA bulk copy of the row instead of 1024 LDG.128 per CTA: under a saturated memory system the
+                    // LDGs took ~2.9 us (in-kernel timeline), the bulk copy of a same-sized activation ~0.5 us.  Each
+                    // thread then reads its block with 16-byte chunks rotated by its lane so the quarter-warps never
+                    // collide on a bank; chunk (j + rot) & 7 lands in v[4j..4j+3].
+                    if (tid == 0) { mbar_arrive_expect_tx(actbar, (uint32_t) K * 4); bulk_g2s(xs, x, (uint32_t) K * 4, actbar); }
+                    if (RING && lane == 0) { gate_done = true; mbar_arrive(actbar + 1); }
+                    mbar_wait(actbar, 0);
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 t = own ? *(const float4 *)(xs + tid * 32 + ((j + rot) & 7) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
+                    }
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 t = own ? *(const float4 *)(x + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
+                    }
+                    if (RING && n == ncols - 1 && lane == 0) { gate_done = true; mbar_arrive(actbar + 1); }
                 }
-                if (RING && n == ncols - 1 && lane == 0) { gate_done = true; mbar_arrive(actbar + 1); }
                 double s4[4] = {0.0, 0.0, 0.0, 0.0};
                 #pragma unroll
                 for (int j = 0; j < 32; j++) s4[j & 3] += widen_nonneg(fmul(v[j], v[j]));
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 if (own) {
                     #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmul(fmul(v[j], scale), wn[j]);
-                    thread_quant_block<WT>(v, an, dn, tid);
+                    thread_quant_block<WT>(v, an, dn, tid, rot);
                 }
             } else {
                 float scale = 1.0f;

@@ -101,7 +101,8 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
     auto kern = k_gemv<WT, G, NC, PRO, EPI, RING>;
     static bool attr_set[16] = {false};
     const size_t stage = (size_t) kQS * TR * CB;
-    const size_t act = (size_t) NC * act_bytes_per_col(a.W.nbq) + 34 * 8 + kWPC * 8 + (size_t) NC * 128 + 64;
+    const size_t act = (size_t) NC * act_bytes_per_col(a.W.nbq) + 34 * 8 + kWPC * 8 + (size_t) NC * 128 + 64 +
+                       ((NC == 1 && PRO == PRO_NORM) ? (size_t) a.W.K * 4 : 0);
     // Ring depth: as deep as possible while EVERY tile of the matrix still gets a co-resident CTA (no second wave):
     // wide matrices (qkv 384 tiles, w1|w3 688) run 3-5 small-ring CTAs per SM, narrow ones (wo, w2: 128 tiles) one
     // CTA per SM with a deep ring.  B200_NS overrides.

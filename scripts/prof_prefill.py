@@ -20,4 +20,9 @@ for mode in (0, 1):
     flops = 2.0 * N * L * (4 * 4096 * 4096 + 3 * 4096 * 11008)
     print("%s prefill: %d tokens x %d layers  %.3f ms  -> %.0f tok/s (32-layer equiv %.0f tok/s), %.1f TFLOP/s" %
           ("fast(tcgen05)" if mode else "exact(dp4a) ", N, L, ms, N / (ms / 1e3), N / (ms * 32 / L / 1e3), flops / (ms / 1e3) / 1e12))
+    sl.profile(True)
+    sl.clear_context(); sl.forward_device(sl.dev_in, N, sl.dev_out)
+    ms_c, cnt = sl.profile_read(); sl.profile(False)
+    names = ("qkv", "rope", "attn", "wo", "w13", "w2", "advance")
+    print("   per class ms (all layers): " + "  ".join("%s %.3f(%d)" % (n, m, c) for n, m, c in zip(names, ms_c, cnt) if c))
 sl.close()
