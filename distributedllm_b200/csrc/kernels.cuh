@@ -149,7 +149,6 @@ struct GemvArgs {
     unsigned long long * trace;          // debug timeline (B200_TRACE), or null
     int pdl_early;                       // trigger dependents at kernel start instead of after the last weight copy
     int pre_stages;                      // ring stages the producer may request before the prologue loads are issued
-    int swp;                             // software-pipelined decode loop
     int dbg_nomath;                      // debug: consume ring stages without computing (streaming-rate probe)
 };
 
@@ -402,84 +401,6 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             for (int n = 0; n < NC; n++) { acc[g][n][0] = 0.f; acc[g][n][1] = 0.f; }
         const uint8_t * gsrc = a.W.data + (long long) tile * a.W.tile_bytes;
 
-#ifdef B200_ENABLE_SWP   // experiment kept for reference: exact, but slower and 160 registers (2 CTAs/SM); see DESIGN.md
-        if (NC == 1 && !a.dbg_nomath && a.swp) {
-            // ---- decode path: software-pipelined over units of PQ quads.  Unit u+1's shared-memory loads
-            // (weights, scales, activation words) are issued into a second register set BEFORE unit u is
-            // computed, so the LDS latency hides behind ~100+ instructions of math; a ring stage is handed back to the
-            // producer as soon as its last unit sits in registers, not when it has been computed.
-            constexpr int PQ = (G == 1) ? 4 : 2;           // quads per unit
-            constexpr int UPS = kQS / PQ;                   // units per stage
-            const int n_unit = n_stage * UPS;
-            uint4 Wb[2][PQ][G], W2b[2][PQ][G]; uint2 Sb[2][PQ][G]; int4 A0[2][PQ], A1[2][PQ]; float4 DA[2][PQ];
-            const int * a_base = a_s + w * 8;
-            auto load_unit = [&](int buf, int u) {
-                const int st = u / UPS, uu = u - st * UPS;
-                const uint8_t * base;
-                if (RING) {
-                    if (uu == 0) mbar_wait(&full[slot], phase);
-                    base = ring + (size_t) slot * stage_bytes;
-                } else base = gsrc + (size_t) st * stage_bytes;
-                base += (size_t)(warp * G) * CB + (size_t)(uu * PQ * TR) * CB;
-                #pragma unroll
-                for (int qi = 0; qi < PQ; qi++) {
-                    #pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const uint8_t * ch = base + (size_t)(qi * TR + g) * CB;
-                        Wb[buf][qi][g] = *(const uint4 *)(ch + lane * 16);
-                        if (WT == kWT_Q8_0) { W2b[buf][qi][g] = *(const uint4 *)(ch + 512 + lane * 16); Sb[buf][qi][g] = *(const uint2 *)(ch + 1024 + r * 8); }
-                        else Sb[buf][qi][g] = *(const uint2 *)(ch + 512 + r * 8);
-                    }
-                    const int Q = u * PQ + qi;
-                    const int4 * ap = (const int4 *)(a_base + Q * 32);
-                    A0[buf][qi] = ap[0]; A1[buf][qi] = ap[1];
-                    DA[buf][qi] = *(const float4 *)(da_s + Q * 4);
-                }
-                if (RING && uu == UPS - 1) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[slot]);
-                    if (++slot == NS) { slot = 0; phase ^= 1; }
-                }
-            };
-            auto compute_unit = [&](int buf) {
-                #pragma unroll
-                for (int qi = 0; qi < PQ; qi++) {
-                    const int4 a01 = A0[buf][qi], a23 = A1[buf][qi];
-                    const float4 dav = DA[buf][qi];
-                    const int alo[4] = {a01.x, a01.z, a23.x, a23.z};
-                    const int ahi[4] = {a01.y, a01.w, a23.y, a23.w};
-                    const float da[4] = {dav.x, dav.y, dav.z, dav.w};
-                    #pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const uint32_t ww[4] = {Wb[buf][qi][g].x, Wb[buf][qi][g].y, Wb[buf][qi][g].z, Wb[buf][qi][g].w};
-                        const uint32_t ww2[4] = {W2b[buf][qi][g].x, W2b[buf][qi][g].y, W2b[buf][qi][g].z, W2b[buf][qi][g].w};
-                        const uint32_t sw[2] = {Sb[buf][qi][g].x, Sb[buf][qi][g].y};
-                        #pragma unroll
-                        for (int bq = 0; bq < 4; bq++) {
-                            const uint16_t dh = (uint16_t)(sw[bq >> 1] >> (16 * (bq & 1)));
-                            const float D = fmul(h2f(dh), da[bq]);
-                            int lo, hi;
-                            if (WT == kWT_Q4_0) { lo = (int)((ww[bq] << 4) & 0xF0F0F0F0u); hi = (int)(ww[bq] & 0xF0F0F0F0u); }
-                            else                { lo = (int) ww[bq]; hi = (int) ww2[bq]; }
-                            const float f0 = fadd(__int_as_float(__dp4a(lo, alo[bq], kMagicI)), -kMagic);
-                            const float f1 = fadd(__int_as_float(__dp4a(hi, ahi[bq], kMagicI)), -kMagic);
-                            acc[g][0][0] = ffma(D, f0, acc[g][0][0]);
-                            acc[g][0][1] = ffma(D, f1, acc[g][0][1]);
-                        }
-                    }
-                }
-            };
-            load_unit(0, 0);
-            for (int u = 0; u < n_unit; u += 2) {
-                if (u + 1 < n_unit) load_unit(1, u + 1);
-                compute_unit(0);
-                if (u + 1 < n_unit) {
-                    if (u + 2 < n_unit) load_unit(0, u + 2);
-                    compute_unit(1);
-                }
-            }
-        } else
-#endif
         for (int s = 0; s < n_stage; s++) {
             const uint8_t * base;
             if (RING) {
@@ -1066,4 +987,121 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
 // position counter kept on the device so a captured graph can be replayed for every token
 __global__ void k_advance(int * n_past, int by) { grid_dep_wait(); if (threadIdx.x == 0) *n_past += by; }
 
+}  // namespace b200
+
+namespace b200 {
+// =============================================================================================
+// lm_head with a Q6_K `output.weight` (what llama.cpp's quantize writes for q4_0 models whose n_embd is a multiple
+// of 256, llama.cpp:2523-2528): exact restatement of ggml_vec_dot_q6_K_q8_K's AVX2 branch (k_quants.c:3484-3561)
+// on activations quantised like quantize_row_q8_K_reference (k_quants.c:1133-1168).
+//   per 256-weight super-block i and AVX lane L (bytes 4L..4L+3 of each 32-byte vector):
+//     S_L = sum_{j<2,k<4} scale[8j+2k+(L>=4)] * sum_{e<4} (q6 - 32) * q8        (all integer)
+//     acc_L = fma(d_i, (float) S_L, acc_L),  d_i = y.d * fp16->f32(x.d);   result = hsum_float_8(acc)
+// Packed layout (k_repack_q6k): per (row, super-block) 288 B = 8 lanes x 8 words of (q6-32) int8x4 in (j,k) order,
+// 16 int8 scales, fp16 d, padding.  Thread (row, L); 32 rows per CTA.
+// =============================================================================================
+constexpr int kWT_Q6_K = 14;
+constexpr int kQ6Packed = 288;
+
+__global__ void k_repack_q6k(const uint8_t * src, uint8_t * dst, int rows, int nb256) {
+    const long long total = (long long) rows * nb256 * 72;       // 72 words per packed block
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int wi = (int)(i % 72); const long long rb = i / 72;
+        const uint8_t * blk = src + rb * 210;                    // ql[128] qh[64] scales[16] d(2)
+        uint32_t out = 0;
+        if (wi < 64) {
+            const int L = wi >> 3, jk = wi & 7, j = jk >> 2, k = jk & 3;
+            for (int e = 0; e < 4; e++) {
+                const int l = 4 * L + e;
+                const uint8_t qlb = blk[64 * j + l + ((k & 1) ? 32 : 0)];
+                const int lo = (k & 2) ? (qlb >> 4) : (qlb & 0xF);
+                const int hi = (blk[128 + 32 * j + l] >> (2 * k)) & 3;
+                out |= ((uint32_t)(((lo | (hi << 4)) - 32) & 0xFF)) << (8 * e);
+            }
+        } else if (wi < 68) {
+            const uint8_t * sc = blk + 192 + (wi - 64) * 4;
+            out = (uint32_t) sc[0] | ((uint32_t) sc[1] << 8) | ((uint32_t) sc[2] << 16) | ((uint32_t) sc[3] << 24);
+        } else if (wi == 68) {
+            out = (uint32_t) blk[208] | ((uint32_t) blk[209] << 8);
+        }
+        ((uint32_t *) dst)[i] = out;
+    }
+}
+
+struct LmHeadQ6Args {
+    const uint8_t * W; int rows, K;
+    const float * x; int ldx; const float * norm_w;
+    float * y; int ldy; int N;
+};
+
+__global__ void __launch_bounds__(256) k_lmhead_q6k(const LmHeadQ6Args a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int nb = a.K / 256, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = blockIdx.y;
+    int * a8 = (int *) smem;                       // [nb][8 jk][8 L] words
+    float * dq = (float *)(a8 + nb * 64);          // [nb]
+    float * ys = dq + nb;                          // [K] normalised activations
+    __shared__ double red[8];
+    __shared__ unsigned long long redk[8];
+    const float * x = a.x + (size_t) n * a.ldx;
+    // RMSNorm * weight (ggml.c:10309-10352, 9062)
+    double s = 0.0;
+    for (int i = tid; i < a.K; i += 256) s += (double) fmul(x[i], x[i]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int i = 0; i < 8; i++) tot += red[i];
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) a.K), 1e-6f)));
+    for (int i = tid; i < a.K; i += 256) ys[i] = fmul(fmul(x[i], scale), a.norm_w[i]);
+    __syncthreads();
+    // quantize_row_q8_K_reference: thread t owns element t of every super-block
+    for (int b = 0; b < nb; b++) {
+        const float v = ys[b * 256 + tid];
+        // first element with the largest magnitude: key = (|v| bits, reversed index)
+        unsigned long long key = ((unsigned long long) __float_as_uint(fabsf(v)) << 32) | (unsigned)(255 - tid);
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o); key = other > key ? other : key; }
+        if (lane == 0) redk[warp] = key;
+        __syncthreads();
+        unsigned long long best = redk[0];
+        for (int i = 1; i < 8; i++) best = redk[i] > best ? redk[i] : best;
+        const int arg = 255 - (int)(best & 0xFFFFFFFFu);
+        const float mx = ys[b * 256 + arg];
+        int q = 0; float d = 0.f;
+        if ((best >> 32) != 0) {
+            const float iscale = __fdiv_rn(-128.f, mx);
+            const float val = fadd(fmul(iscale, v), 12582912.f);                 // nearest_int (k_quants.c:50-55)
+            q = min(127, (int)((__float_as_uint(val) & 0x007fffffu) - 0x00400000));
+            d = __fdiv_rn(1.0f, iscale);
+        }
+        // element t = 128 j + 32 k + 4 L + e  ->  byte e of word [jk][L]
+        const int j = tid >> 7, k = (tid >> 5) & 3, L = (tid >> 2) & 7, e = tid & 3;
+        uint32_t pk = ((uint32_t)(q & 0xFF)) << (8 * e);
+        pk |= __shfl_xor_sync(0xffffffffu, pk, 1);
+        pk |= __shfl_xor_sync(0xffffffffu, pk, 2);
+        if (e == 0) a8[b * 64 + (j * 4 + k) * 8 + L] = (int) pk;
+        if (tid == 0) dq[b] = d;
+        __syncthreads();
+    }
+    const int row = blockIdx.x * 32 + (tid >> 3), L = tid & 7;
+    float acc = 0.f;
+    if (row < a.rows) {
+        const uint8_t * wrow = a.W + (size_t) row * nb * kQ6Packed;
+        for (int b = 0; b < nb; b++) {
+            const uint4 * wp = (const uint4 *)(wrow + (size_t) b * kQ6Packed + L * 32);
+            const uint4 w0 = wp[0], w1 = wp[1];
+            const uint32_t ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const int8_t * sc = (const int8_t *)(wrow + (size_t) b * kQ6Packed + 256);
+            const float dw = h2f(*(const uint16_t *)(wrow + (size_t) b * kQ6Packed + 272));
+            int S = 0;
+            #pragma unroll
+            for (int jk = 0; jk < 8; jk++)
+                S += (int) sc[2 * jk + (L >> 2)] * __dp4a((int) ww[jk], a8[b * 64 + jk * 8 + L], 0);
+            acc = ffma(fmul(dq[b], dw), (float) S, acc);
+        }
+    }
+    acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+    acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+    acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+    if (L == 0 && row < a.rows) a.y[(size_t) n * a.ldy + row] = acc;
+}
 }  // namespace b200

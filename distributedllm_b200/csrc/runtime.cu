@@ -125,7 +125,7 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[s->device & 15] = true;
     }
-    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pdl_early = env_int("B200_PDL_EARLY", 0); a.swp = env_int("B200_SWP", 0); a.pre_stages = env_int("B200_PRE", 2);
+    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pdl_early = env_int("B200_PDL_EARLY", 0); a.pre_stages = env_int("B200_PRE", 2);
     a.trace = nullptr;
     if (s->trace && s->trace_next < 512) { a.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(s->cur_class); }
     int per_sm = s->opt_cta_per_sm > 0 ? s->opt_cta_per_sm : (int)(kSmemLimit / (smem + 1024));
@@ -938,7 +938,7 @@ struct b200_extra {
     int n_vocab = 0, E = 0, emb_type = 0, out_type = 0;
     uint8_t * emb_raw = nullptr;          // tok_embeddings as stored (row = token)
     float * norm_w = nullptr;
-    PackedW out{}; uint16_t * out_f16 = nullptr;
+    PackedW out{}; uint16_t * out_f16 = nullptr; uint8_t * out_q6k = nullptr;
     float * d_x = nullptr, * d_logits = nullptr; int32_t * d_tok = nullptr; int cap_tokens = 0;
     std::vector<std::pair<std::string, float>> vocab;
     std::unordered_map<std::string, int> token_to_id;
@@ -1051,16 +1051,22 @@ int b200_extra_load(const char * path, int device, b200_extra_t ** out) {
         e->emb_type = (int) te.type; e->out_type = (int) to.type;
         if (te.type != GT_Q4_0 && te.type != GT_Q8_0 && te.type != GT_F16 && te.type != GT_F32)
             return fail(B200_EFILE, "tok_embeddings type %u unsupported", te.type);
-        if (to.type != GT_Q4_0 && to.type != GT_Q8_0 && to.type != GT_F16)
-            return fail(B200_EFILE, "output.weight type %u unsupported (Q4_0, Q8_0, F16; the Q6_K lm_head llama.cpp's quantize writes for "
-                                    "n_embd %% 256 == 0 is not implemented yet)", to.type);
+        if (to.type != GT_Q4_0 && to.type != GT_Q8_0 && to.type != GT_F16 && to.type != GT_Q6_K)
+            return fail(B200_EFILE, "output.weight type %u unsupported (Q4_0, Q8_0, F16, Q6_K)", to.type);
+        if (to.type == GT_Q6_K && E % 256) return fail(B200_EFILE, "Q6_K output.weight needs n_embd %% 256 == 0");
         if (tn.type != GT_F32) return fail(B200_EFILE, "norm.weight must be F32");
         if ((rc = dev_alloc(s, &e->emb_raw, te.nbytes)) || (rc = dev_alloc(s, &e->norm_w, (size_t) E))) return rc;
         B200_CUDA(cudaMemcpyAsync(e->emb_raw, f.data(te), te.nbytes, cudaMemcpyHostToDevice, s->stream));
         B200_CUDA(cudaMemcpyAsync(e->norm_w, f.data(tn), (size_t) E * 4, cudaMemcpyHostToDevice, s->stream));
         uint8_t * scratch = nullptr;
         B200_CUDA(cudaMalloc((void **) &scratch, to.nbytes + 4096));
-        if (to.type == GT_F16) rc = pack_f16(s, f, to, scratch, &e->out_f16);
+        if (to.type == GT_Q6_K) {
+            const int nb256 = (int) E / 256;
+            if (!(rc = dev_alloc(s, &e->out_q6k, (size_t) V * nb256 * kQ6Packed)) && !(rc = upload_raw(s, f, to, scratch))) {
+                k_repack_q6k<<<s->n_sm * 8, 256, 0, s->stream>>>(scratch, e->out_q6k, (int) V, nb256);
+                if (cudaGetLastError() != cudaSuccess) rc = fail(B200_ECUDA, "k_repack_q6k launch failed");
+            }
+        } else if (to.type == GT_F16) rc = pack_f16(s, f, to, scratch, &e->out_f16);
         else { const GgjtTensor * src[1] = {&to}; rc = pack_matrix(s, f, src, 1, 0, 1, scratch, &e->out); }
         B200_CUDA(cudaStreamSynchronize(s->stream));
         cudaFree(scratch);
@@ -1117,6 +1123,16 @@ static int extra_logits_device(b200_extra * e, const float * emb, int n_tokens) 
     int rc = extra_reserve(e, n_tokens);
     if (rc) return rc;
     B200_CUDA(cudaMemcpyAsync(e->d_x, emb, (size_t) n_tokens * e->E * 4, cudaMemcpyHostToDevice, s->stream));
+    if (e->out_type == kWT_Q6_K) {
+        LmHeadQ6Args q{e->out_q6k, e->n_vocab, e->E, e->d_x, e->E, e->norm_w, e->d_logits, e->n_vocab, n_tokens};
+        const size_t smem = (size_t)(e->E / 256) * (64 * 4 + 4) + (size_t) e->E * 4 + 64;
+        static bool attr_set[16] = {false};
+        if (!attr_set[s->device & 15]) {
+            B200_CUDA(cudaFuncSetAttribute(k_lmhead_q6k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[s->device & 15] = true;
+        }
+        return launch_simple(s, k_lmhead_q6k, dim3((e->n_vocab + 31) / 32, n_tokens, 1), dim3(256, 1, 1), smem, q);
+    }
     if (e->out_type == kWT_F16) {
         GemvF16Args f{}; f.K = e->E; f.x = e->d_x; f.ldx = e->E; f.norm_w = e->norm_w; f.N = n_tokens;
         f.rows = e->n_vocab; f.W = e->out_f16; f.y = e->d_logits; f.ldy = e->n_vocab;

@@ -65,6 +65,22 @@ def main():
                         logits_last=oracle.ref_logits(extra, h, sh.n_vocab, False),
                         file_sha256=np.frombuffer(hashlib.sha256(open(extra, "rb").read()).digest(), np.uint8))
 
+    # extra layers as the reference's own `quantize q4_0` writes them for n_embd % 256 == 0: output.weight is Q6_K
+    # (llama.cpp:2523-2528).  The quantised file itself is committed (190 KB): k-quant quantisation is not restated here.
+    import subprocess
+    full = os.path.join(tmp, "full_f32.bin")
+    ggjt.write_synth_full(full, sh, ggjt.T_F32, seed=0)
+    fq = os.path.join(tmp, "full_q4.bin")
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "quantize"), full, fq, "q4_0"], check=True, capture_output=True)
+    eq = os.path.join(HERE, "extra_q6k.bin")
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "slice_model"), "extra_layers", fq, eq], check=True, capture_output=True)
+    assert ggjt.read_file(eq).tensors["output.weight"].ttype == ggjt.T_Q6_K
+    h6 = np.random.default_rng(8).standard_normal((6, sh.n_embd), dtype=np.float32)
+    h6[3] *= 30.0
+    h6[4, :] = 0.0
+    np.savez_compressed(os.path.join(HERE, "extra_q6k.npz"), hidden=h6, logits_all=oracle.ref_logits(eq, h6, sh.n_vocab, True),
+                        emb=oracle.ref_embed(eq, toks, sh.n_embd), tokens=toks)
+
     # tokenizer with the real 32000-entry llama vocabulary
     vocab_bin = "/root/reference/vendor/llama.cpp/models/ggml-vocab.bin"
     f = ggjt.read_file(vocab_bin, sliced=False)

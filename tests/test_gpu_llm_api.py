@@ -71,6 +71,18 @@ def test_extra_layers_match_reference_goldens(llm, tmp_path):
     assert llm.decode_token(extra, 1) == "<s>"
 
 
+def test_q6k_lm_head_matches_reference_goldens(llm):
+    """The extra-layers file exactly as the reference's `quantize q4_0` + `slice_model extra_layers` produce it
+    (Q6_K output.weight): logits bit-identical to the reference's get_llm_output."""
+    g = np.load(os.path.join(GOLD, "extra_q6k.npz"))
+    extra = os.path.join(GOLD, "extra_q6k.bin")
+    hid = g["hidden"]
+    la = np.array(llm.get_logits(extra, hid.ravel().tolist(), True), np.float32).reshape(len(hid), -1)
+    assert (_bits(la) == _bits(g["logits_all"])).all(), int((_bits(la) != _bits(g["logits_all"])).sum())
+    emb = np.array(llm.prepare_embeddings(extra, g["tokens"].tolist()), np.float32).reshape(len(g["tokens"]), -1)
+    assert (_bits(emb) == _bits(g["emb"])).all()
+
+
 def test_tokenizer_matches_reference_goldens(llm, tmp_path):
     gold = json.load(open(os.path.join(GOLD, "tokenizer.json")))
     raw = gzip.open(os.path.join(GOLD, "llama_vocab.bin.gz")).read()

@@ -63,11 +63,13 @@ def test_decode_only_long(tmp_models, shape):
     assert bad == 0
 
 
-@pytest.mark.parametrize("pdl,graph", [("0", "1"), ("1", "0"), ("0", "0")])
-def test_launch_modes_agree(tmp_models, monkeypatch, pdl, graph):
-    """Programmatic dependent launch and CUDA-graph replay are scheduling choices only."""
+@pytest.mark.parametrize("pdl,graph,nq", [("0", "1", "0"), ("1", "0", "0"), ("0", "0", "0"), ("1", "1", "1"), ("0", "0", "1")])
+def test_launch_modes_agree(tmp_models, monkeypatch, pdl, graph, nq):
+    """Programmatic dependent launch, CUDA-graph replay and the grid-barrier norm+quant epilogue (B200_NQ) are
+    scheduling / fusion choices only: all stay bit-exact."""
     monkeypatch.setenv("B200_PDL", pdl)
     monkeypatch.setenv("B200_GRAPH", graph)
+    monkeypatch.setenv("B200_NQ", nq)
     sh = ggjt.SHAPES["tiny128"]
     path = tmp_models("tiny128", ggjt.T_Q4_0, 0, 2)
     bad, tot = _run_pair(path, [37, 1, 1, 1, 30, 1, 1], sh)
