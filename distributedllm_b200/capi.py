@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
         L.b200_slice_profile_read.argtypes = [vp, vp, vp, ci]
         L.b200_debug_read.argtypes = [vp, ci, C.c_size_t, C.c_size_t, vp]
         L.b200_debug_trace_enable.argtypes = [vp, ci]
+        L.b200_debug_skip_attention.argtypes = [vp, ci]
         L.b200_debug_trace_read.argtypes = [vp, vp, vp, vp, ci]
         L.b200_slice_dev_in.argtypes = [vp]
         L.b200_slice_dev_in.restype = vp
@@ -163,6 +164,9 @@ class Slice:
         out = np.zeros(count, np.uint32)
         check(lib().b200_debug_read(self._h, which, 0, count, _ptr(out)))
         return out.view(dtype)
+
+    def skip_attention(self, on: bool) -> None:
+        check(lib().b200_debug_skip_attention(self._h, int(on)))
 
     def trace_enable(self, on: bool) -> None:
         check(lib().b200_debug_trace_enable(self._h, int(on)))

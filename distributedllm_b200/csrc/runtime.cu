@@ -27,7 +27,7 @@ struct LayerW {
     float * attn_norm = nullptr, * ffn_norm = nullptr;
 };
 
-struct GraphKey { const float * in; float * out; bool host; bool operator<(const GraphKey & o) const {
+struct GraphKey { const float * in; float * out; int host; bool operator<(const GraphKey & o) const {
     return in != o.in ? in < o.in : (out != o.out ? out < o.out : host < o.host); } };
 
 }  // namespace b200
@@ -54,6 +54,7 @@ struct b200_slice {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
     int64_t launches = 0, weight_bytes = 0;
     bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true;
+    bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
     int opt_ns = 0, opt_qs = 0, opt_cta_per_sm = 0;
     std::mutex mu;
@@ -245,7 +246,9 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             if (il > 0 && nq) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_STORE>(s, g))) return rc; }
             else                     { if ((rc = launch_gemv<1, PRO_NORM, EPI_STORE>(s, g))) return rc; }
         }
-        if (D == 128) {
+        if (s->skip_attention) {
+            // measurement aid: the matmul kernels of the step back to back, attention left out
+        } else if (D == 128) {
             // head size 128: cluster kernel; for N = 1 RoPE + KV append are fused into its prologue
             constexpr int kChunk = 32;
             const size_t asm_bytes = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + 64;
@@ -352,7 +355,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
 
 // N = 1: replay a captured graph (host variant adds the H2D / D2H copies as graph nodes)
 static int run_decode_graph(b200_slice * s, const float * in, float * out, bool host) {
-    GraphKey key{in, out, host};
+    GraphKey key{in, out, (host ? 1 : 0) | (s->skip_attention ? 2 : 0)};
     auto it = s->graphs.find(key);
     const int per_step = (s->D == 128 ? 5 : 6) * s->L + (s->wtype == kWT_F16 ? 2 * s->L : 0) + 1;
     if (it == s->graphs.end()) {
@@ -720,6 +723,15 @@ int b200_slice_set_fast_prefill(b200_slice_t * s, int on, int min_tokens) {
     std::lock_guard<std::mutex> lk(s->mu);
     s->fast_prefill = on != 0;
     if (min_tokens > 0) s->fast_min_tokens = min_tokens;
+    return 0;
+}
+
+/* Measurement aid for bench.py's roofline: while on, a decode step launches ONLY its weight-matmul kernels (the
+ * attention launch is skipped, so hidden states are meaningless and the KV cache is not appended). */
+int b200_debug_skip_attention(b200_slice_t * s, int on) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->skip_attention = on != 0;
     return 0;
 }
 

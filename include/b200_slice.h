@@ -111,6 +111,9 @@ float * b200_slice_dev_out(b200_slice_t * s);
  * (0 qkv, 1 att, 2 ffin, 3 gate, 4 xa, 5 xb, 6 q16, 7 k-cache, 8 v-cache).  Not part of the drop-in surface. */
 int b200_debug_read(b200_slice_t * s, int which, size_t offset_words, size_t count, void * out);
 
+/* Measurement aid (bench.py roofline): while on, a decode step launches only its weight-matmul kernels. */
+int b200_debug_skip_attention(b200_slice_t * s, int on);
+
 /* In-kernel %globaltimer timeline of the matmul / attention launches (8 stamps per CTA: [0] entry, [1] dependency
  * resolved, [2] prologue done, [3] exit, [4] last weight copy issued).  _enable(1) re-captures the decode graph with
  * tracing; _read returns the launches recorded so far (class ids as in b200_slice_profile_read). */
