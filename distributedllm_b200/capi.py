@@ -40,6 +40,15 @@ def lib() -> C.CDLL:
         L.b200_last_error.restype = C.c_char_p
         L.b200_version.restype = C.c_char_p
         L.b200_slice_load.argtypes = [C.c_char_p, ci, ci, C.POINTER(vp)]
+        L.b200_slice_load_ex.argtypes = [C.c_char_p, ci, ci, ci, C.POINTER(vp)]
+        L.b200_session_count.argtypes = [vp]
+        L.b200_session_n_past.argtypes = [vp, ci]
+        L.b200_session_clear.argtypes = [vp, ci]
+        L.b200_session_rewind.argtypes = [vp, ci, ci]
+        L.b200_session_forward.argtypes = [vp, ci, vp, ci, vp]
+        L.b200_session_forward_device.argtypes = [vp, ci, vp, ci, vp, ci]
+        L.b200_batch_forward.argtypes = [vp, vp, ci, vp, vp]
+        L.b200_batch_forward_device.argtypes = [vp, vp, ci, vp, vp, ci]
         L.b200_slice_unload.argtypes = [vp]
         L.b200_slice_clear.argtypes = [vp]
         L.b200_slice_rewind.argtypes = [vp, ci]
@@ -66,7 +75,8 @@ def lib() -> C.CDLL:
         L.b200_slice_dev_out.argtypes = [vp]
         L.b200_slice_dev_out.restype = vp
         for name, args in (("b200_pipeline_unique_id", [vp]), ("b200_pipeline_init", [vp, ci, ci, vp]),
-                           ("b200_pipeline_step", [vp, vp, ci, ci]), ("b200_pipeline_destroy", [vp]),
+                           ("b200_pipeline_step", [vp, vp, ci, ci]),
+                           ("b200_pipeline_step_session", [vp, ci, vp, ci, ci]), ("b200_pipeline_step_batch", [vp, vp, ci, vp, ci]), ("b200_pipeline_destroy", [vp]),
                            ("b200_extra_load", [C.c_char_p, ci, C.POINTER(vp)]), ("b200_extra_unload", [vp]),
                            ("b200_extra_dims", [vp, C.POINTER(ci), C.POINTER(ci)]),
                            ("b200_extra_embed", [vp, vp, ci, vp]), ("b200_extra_logits", [vp, vp, ci, ci, vp]),
@@ -93,10 +103,39 @@ def _ptr(a: np.ndarray) -> C.c_void_p:
 class Slice:
     """One slice resident on one GPU (mirrors llm.load_slice / propagate_forward / clear_context)."""
 
-    def __init__(self, path: str, device: int = 0, n_ctx: int = 0):
+    def __init__(self, path: str, device: int = 0, n_ctx: int = 0, n_sessions: int = 1):
         self._h = C.c_void_p()
-        check(lib().b200_slice_load(os.fsencode(path), device, n_ctx, C.byref(self._h)))
+        check(lib().b200_slice_load_ex(os.fsencode(path), device, n_ctx, n_sessions, C.byref(self._h)))
         self.info = self._info()
+        self.n_sessions = n_sessions
+
+    # ---- sessions / batched steps (additive API, include/b200_slice.h) ----
+    def session_forward(self, session: int, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, self.n_embd)
+        out = np.empty_like(x)
+        check(lib().b200_session_forward(self._h, session, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def batch_forward(self, sessions, x: np.ndarray) -> np.ndarray:
+        """One token for each listed session: x is [len(sessions)][n_embd]."""
+        ids = np.ascontiguousarray(sessions, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(len(ids), self.n_embd)
+        out = np.empty_like(x)
+        check(lib().b200_batch_forward(self._h, _ptr(ids), len(ids), _ptr(x), _ptr(out)))
+        return out
+
+    def batch_forward_device(self, sessions, d_in: int, d_out: int, sync: bool = False) -> None:
+        ids = np.ascontiguousarray(sessions, dtype=np.int32)
+        check(lib().b200_batch_forward_device(self._h, _ptr(ids), len(ids), C.c_void_p(d_in), C.c_void_p(d_out), int(sync)))
+
+    def session_n_past(self, session: int) -> int:
+        return lib().b200_session_n_past(self._h, session)
+
+    def session_clear(self, session: int = -1) -> None:
+        check(lib().b200_session_clear(self._h, session))
+
+    def session_rewind(self, session: int, n_past: int) -> None:
+        check(lib().b200_session_rewind(self._h, session, n_past))
 
     def _info(self) -> SliceInfo:
         i = SliceInfo()

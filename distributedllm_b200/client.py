@@ -74,9 +74,15 @@ class Sampler:
 
 
 class DistributedLLM:
-    def __init__(self, addresses: Sequence[Tuple[str, int]], extra_layers_path: str):
+    def __init__(self, addresses: Sequence[Tuple[str, int]], extra_layers_path: str, wire: str = "list"):
+        """wire: "list"  -- the reference's per-node star of float lists (common.py:148-154);
+                 "bytes" -- same star, tensors as one binary field;
+                 "chain" -- binary, and the nodes pass the activation along themselves: one client round trip per step."""
+        if wire not in ("list", "bytes", "chain"):
+            raise ValueError("wire must be list, bytes or chain")
         self.addresses = list(addresses)
         self.extra_layers_path = extra_layers_path
+        self.wire = wire
         self.llm = import_llm()
 
     def generate(self, prompt, max_steps=200, temperature=0.0, repeat_penalty=1.1):
@@ -119,9 +125,18 @@ class DistributedLLM:
 
     def propagate_tensor(self, embeddings):
         shape = (1, len(embeddings))
-        for address in self.addresses:
-            embeddings = Connection(address).propagate_forward(embeddings, shape)["values"]
-        return embeddings
+        if self.wire == "list":
+            for address in self.addresses:
+                embeddings = Connection(address).propagate_forward(embeddings, shape)["values"]
+            return embeddings
+        x = np.asarray(embeddings, dtype=np.float32)
+        if self.wire == "bytes":
+            for address in self.addresses:
+                x = Connection(address).propagate_forward_bytes(x, shape)
+        else:
+            route = ["%s:%d" % (h, p) for h, p in self.addresses[1:]]
+            x = Connection(self.addresses[0]).propagate_forward_bytes(x, shape, route)
+        return x.tolist()
 
 
 class LocalPipeline:

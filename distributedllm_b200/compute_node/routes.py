@@ -9,6 +9,9 @@ Same request names, same replies, same error codes:
   request_file_submission_end   -> file_submission_end_response | operation_failure(upload_not_found | file_upload_failed)
   propagate_forward_request     -> tensor_response | operation_failure(neural_computation_error | slice_not_loaded)
   clear_context_request         -> clear_context_response | operation_failure(clear_context_failure)
+Additive:
+  propagate_bytes_request       -> tensor_bytes_response | operation_failure(... | chain_hop_failed): binary tensor, and
+                                   node-to-node chaining along `route` so the client makes ONE round trip per step
 """
 from __future__ import annotations
 
@@ -118,6 +121,45 @@ def handle_propagate_forward(ctx, message):
         return _failure(message, "slice_not_loaded")
     axis0, axis1 = out.shape
     return protocol.ResponsePropagateForward(axis0, axis1, out.values)
+
+
+def parse_hop(hop: str):
+    host, _, port = hop.rpartition(":")
+    return host, int(port)
+
+
+@route("propagate_bytes_request")
+def handle_propagate_bytes(ctx, message):
+    import numpy as np
+    if len(message.data) % 4:
+        return _failure(message, "neural_computation_error", "tensor is not a whole number of float32")
+    tensor = Tensor((message.axis0, message.axis1), np.frombuffer(message.data, dtype=np.float32))
+    try:
+        out = ctx.slice_container.forward(tensor)
+    except NeuralComputationError:
+        return _failure(message, "neural_computation_error")
+    except SliceNotLoadedError:
+        return _failure(message, "slice_not_loaded")
+    data = np.ascontiguousarray(out.values, dtype=np.float32).tobytes()
+    try:
+        hops = json.loads(message.route) if message.route else []
+    except ValueError:
+        return _failure(message, "chain_hop_failed", "unparsable route")
+    if not hops:
+        return protocol.ResponsePropagateBytes(out.shape[0], out.shape[1], data)
+    # hand the activation to the next node ourselves and relay whatever comes back (a tensor or a failure)
+    try:
+        import socket
+        with socket.create_connection(parse_hop(hops[0]), timeout=ctx_timeout(ctx)) as sock:
+            protocol.RequestPropagateBytes(out.shape[0], out.shape[1], data, json.dumps(hops[1:])).send(sock)
+            name, body = protocol.receive_message(sock)
+        return protocol.restore_message(name, body)
+    except Exception as e:      # unreachable / misbehaving next hop
+        return _failure(message, "chain_hop_failed", "%s: %r" % (hops[0], e))
+
+
+def ctx_timeout(ctx):
+    return getattr(ctx, "hop_timeout", 120.0)
 
 
 @route("clear_context_request")

@@ -26,9 +26,10 @@ def restore_registry(ctx: RequestContext, uploads_dir: str) -> None:
 
 class _Handler(socketserver.BaseRequestHandler):
     uploads_dir = "uploads"
+    context = None          # an explicit RequestContext (several nodes in one process); None = process-wide singleton
 
     def handle(self):
-        TCPHandler(self.request, RequestContext.production(self.uploads_dir, FUNKY_NAMES)).handle()
+        TCPHandler(self.request, self.context or RequestContext.production(self.uploads_dir, FUNKY_NAMES)).handle()
 
 
 class ThreadingTCPServer(socketserver.ThreadingMixIn, socketserver.TCPServer):
@@ -36,10 +37,10 @@ class ThreadingTCPServer(socketserver.ThreadingMixIn, socketserver.TCPServer):
     daemon_threads = True
 
 
-def make_server(host: str, port: int, uploads_dir: str) -> ThreadingTCPServer:
-    ctx = RequestContext.production(uploads_dir, FUNKY_NAMES)
+def make_server(host: str, port: int, uploads_dir: str, context: RequestContext = None) -> ThreadingTCPServer:
+    ctx = context or RequestContext.production(uploads_dir, FUNKY_NAMES)
     restore_registry(ctx, uploads_dir)
-    handler = type("NodeHandler", (_Handler,), {"uploads_dir": uploads_dir})
+    handler = type("NodeHandler", (_Handler,), {"uploads_dir": uploads_dir, "context": context})
     return ThreadingTCPServer((host, port), handler)
 
 

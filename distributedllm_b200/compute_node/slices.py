@@ -57,6 +57,9 @@ class DummySlice(ModelSlice):
         self.k, self.b = k, b
 
     def __call__(self, tensor: Tensor) -> Tensor:
+        if hasattr(tensor.values, "dtype"):
+            import numpy as np
+            return Tensor(tensor.shape, (np.float64(self.k) * tensor.values.astype(np.float64) + self.b).astype(np.float32))
         return Tensor(tensor.shape, [self.k * v + self.b for v in tensor.values])
 
 
@@ -69,6 +72,14 @@ class GGMLSlice(ModelSlice):
         self.llm.load_slice(self.path)
 
     def __call__(self, tensor: Tensor) -> Tensor:
+        if hasattr(tensor.values, "dtype"):
+            # binary wire format: float32 buffer in, bytes out, no per-float Python objects (llm.propagate_forward_buffer)
+            import numpy as np
+            try:
+                out = self.llm.propagate_forward_buffer(np.ascontiguousarray(tensor.values, dtype=np.float32))
+            except RuntimeError as e:            # the buffer entry point raises where the list one returns a status
+                raise NeuralComputationError(str(e))
+            return Tensor(tensor.shape, np.frombuffer(out, dtype=np.float32))
         out = self.llm.propagate_forward(tensor.values)
         if not isinstance(out, list):
             raise NeuralComputationError("slice forward failed with status %r" % (out,))

@@ -138,6 +138,24 @@ class Connection:
         return {"shape": [reply.axis0, reply.axis1], "values": reply.values}
 
 
+    def propagate_forward_bytes(self, tensor, shape, route=()):
+        """Binary wire format (additive): `tensor` is a float32 numpy array / buffer; `route` lists the "host:port" hops
+        the node should forward to on its own.  Returns a float32 numpy array (the LAST hop's output)."""
+        import json
+        import numpy as np
+        axis0, axis1 = shape
+        data = np.ascontiguousarray(tensor, dtype=np.float32).tobytes()
+        reply = self._get_response(protocol.RequestPropagateBytes(axis0, axis1, data, json.dumps(list(route))))
+        kind = reply.get_message()
+        if kind == "operation_failure":
+            raise OperationFailedError("%s: %s" % (reply.error, reply.description))
+        if kind != "tensor_bytes_response":
+            raise Exception("Cannot handle unrecognized message")
+        if (reply.axis0, reply.axis1) != (shape[0], shape[1]):
+            raise OperationFailedError
+        return np.frombuffer(reply.data, dtype=np.float32)
+
+
 class ControlCenter:
     """Status book-keeping over a nodes map {name: (ip, port)} (reference: control_center.py:8-71)."""
 

@@ -553,6 +553,56 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
 }
 
 // =============================================================================================
+// K3: RMSNorm * weight -> Q8_0 act-quant of whole rows, once per token, for MULTI-token calls (prefill chunks, batched
+// steps).  With several columns per CTA the fused PRO_NORM prologue would repeat this for every 32-row tile (480x for
+// qkv) behind one dependent global round trip per column; here it is done once and the matmul CTAs fetch the quantised
+// columns with a bulk copy (PRO_PREQ).  Same per-block arithmetic as the fused prologue (thread_quant_block).
+// Single-token steps keep the fused prologue: there the extra launch would cost more than the redundancy.
+// =============================================================================================
+struct NormQuantArgs {
+    const float * x; int ldx; const float * norm_w; int K;
+    int * aq; float * da; int nbq;            // [N][nbq*32] words, [N][nbq*4] scales (x 1/16 for Q4_0 weights)
+};
+
+template <int WT>
+__global__ void __launch_bounds__(256) k_norm_quant(const NormQuantArgs a) {
+    __shared__ double red[8];
+    const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nb = a.K / 32;
+    if (tid == 0) grid_dep_launch();
+    grid_dep_wait();
+    const float * x = a.x + (size_t) n * a.ldx;
+    double s = 0.0;
+    for (int b = tid; b < nb; b += 256) {
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 t = *(const float4 *)(x + b * 32 + j * 4);
+            s += widen_nonneg(fmul(t.x, t.x)); s += widen_nonneg(fmul(t.y, t.y));
+            s += widen_nonneg(fmul(t.z, t.z)); s += widen_nonneg(fmul(t.w, t.w));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    double tot = 0.0;
+    #pragma unroll
+    for (int i = 0; i < 8; i++) tot += red[i];
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) a.K), 1e-6f)));
+    int * an = a.aq + (size_t) n * a.nbq * 32;
+    float * dn = a.da + (size_t) n * a.nbq * 4;
+    for (int b = tid; b < nb; b += 256) {
+        float v[32];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 t = *(const float4 *)(x + b * 32 + j * 4);
+            const float4 wv = *(const float4 *)(a.norm_w + b * 32 + j * 4);
+            v[j*4]   = fmul(fmul(t.x, scale), wv.x); v[j*4+1] = fmul(fmul(t.y, scale), wv.y);
+            v[j*4+2] = fmul(fmul(t.z, scale), wv.z); v[j*4+3] = fmul(fmul(t.w, scale), wv.w);
+        }
+        thread_quant_block<WT>(v, an, dn, b);
+    }
+}
+
+// =============================================================================================
 // K1f: F16-weight matmul, exact mode: ggml_vec_dot_f16 (32 f32 slots, chunks of 32 in order,
 // fixed reduce tree, n%32 tail in double).  One warp per output row, lane = slot; weights are
 // re-laid at load as [row][c8 = chunk/8][lane][8 chunks] so each lane issues one 16 B load per
@@ -604,15 +654,22 @@ __global__ void __launch_bounds__(256) k_gemv_f16(const GemvF16Args a) {
             const uint16_t * tl = m ? a.tail2 : a.tail;
             float acc = 0.f;
             const uint4 * wp = (const uint4 *)(Wm + ((size_t) row * nc8 * 32 + lane) * 8);
-            for (int c8 = 0; c8 < nc8; c8++) {
-                const uint4 v = wp[(size_t) c8 * 32];
-                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+            // 4 x 16 B per lane in flight (2 KB per warp): the FMA chain stays in chunk order, the loads run ahead
+            constexpr int U = 4;
+            for (int c8 = 0; c8 < nc8; c8 += U) {
+                uint4 v[U];
                 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int c = c8 * 8 + j;
-                    if (c < nchunk) {
-                        const uint16_t wh = (uint16_t)(u[j >> 1] >> (16 * (j & 1)));
-                        acc = ffma(h2f(wh), h2f(xh[c * 32 + lane]), acc);
+                for (int q = 0; q < U; q++) v[q] = c8 + q < nc8 ? __ldcs(wp + (size_t)(c8 + q) * 32) : make_uint4(0, 0, 0, 0);
+                #pragma unroll
+                for (int q = 0; q < U; q++) {
+                    const uint32_t u[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int c = (c8 + q) * 8 + j;
+                        if (c < nchunk) {
+                            const uint16_t wh = (uint16_t)(u[j >> 1] >> (16 * (j & 1)));
+                            acc = ffma(h2f(wh), h2f(xh[c * 32 + lane]), acc);
+                        }
                     }
                 }
             }
@@ -661,12 +718,16 @@ struct RopeArgs {
     const int * n_past;
     const float2 * cs;            // [n_ctx][D/2] (cos, sin)
     uint16_t * q16; uint16_t * kc; uint16_t * vc;   // kc/vc: this layer's cache base
+    const int2 * cols; size_t sess_stride;          // batched step: column n = (session, position); cache base += session * stride
 };
 
 __global__ void k_rope_append(const RopeArgs a) {
     grid_dep_launch();
     grid_dep_wait();
-    const int n = blockIdx.y, pos = *a.n_past + n, half = a.D / 2;
+    const int n = blockIdx.y, half = a.D / 2;
+    int pos; uint16_t * kcb = a.kc, * vcb = a.vc;
+    if (a.cols) { const int2 c = a.cols[n]; pos = c.y; kcb += (size_t) c.x * a.sess_stride; vcb += (size_t) c.x * a.sess_stride; }
+    else pos = *a.n_past + n;
     const float * row = a.qkv + (size_t) n * 3 * a.E;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.E / 2; p += gridDim.x * blockDim.x) {
         const int j = p % half;
@@ -677,8 +738,8 @@ __global__ void k_rope_append(const RopeArgs a) {
         const float q0 = fsub(fmul(q.x, cs.x), fmul(q.y, cs.y)), q1 = fadd(fmul(q.x, cs.y), fmul(q.y, cs.x));
         const float k0 = fsub(fmul(k.x, cs.x), fmul(k.y, cs.y)), k1 = fadd(fmul(k.x, cs.y), fmul(k.y, cs.x));
         *(uint32_t *)(a.q16 + (size_t) n * a.E + 2 * p) = (uint32_t) f2h(q0) | ((uint32_t) f2h(q1) << 16);
-        *(uint32_t *)(a.kc + (size_t) pos * a.E + 2 * p) = (uint32_t) f2h(k0) | ((uint32_t) f2h(k1) << 16);
-        *(uint32_t *)(a.vc + (size_t) pos * a.E + 2 * p) = (uint32_t) f2h(v.x) | ((uint32_t) f2h(v.y) << 16);
+        *(uint32_t *)(kcb + (size_t) pos * a.E + 2 * p) = (uint32_t) f2h(k0) | ((uint32_t) f2h(k1) << 16);
+        *(uint32_t *)(vcb + (size_t) pos * a.E + 2 * p) = (uint32_t) f2h(v.x) | ((uint32_t) f2h(v.y) << 16);
     }
 }
 
@@ -696,6 +757,7 @@ struct AttnArgs {
     const uint16_t * texp;
     float * out;                  // [N][E]
     float kq_scale;
+    const int2 * cols; size_t sess_stride;   // batched step (independent sequences): column n = (session, position), T = position + 1
 };
 
 __global__ void __launch_bounds__(512) k_attention(const AttnArgs a) {
@@ -703,7 +765,9 @@ __global__ void __launch_bounds__(512) k_attention(const AttnArgs a) {
     grid_dep_launch();
     grid_dep_wait();
     const int h = blockIdx.x, n = blockIdx.y, D = a.D, E = a.E;
-    const int n_past = *a.n_past, T = n_past + a.N, tcount = n_past + n + 1;
+    int T, tcount; const uint16_t * kcb = a.kc, * vcb = a.vc;
+    if (a.cols) { const int2 c = a.cols[n]; T = tcount = c.y + 1; kcb += (size_t) c.x * a.sess_stride; vcb += (size_t) c.x * a.sess_stride; }
+    else { const int n_past = *a.n_past; T = n_past + a.N; tcount = n_past + n + 1; }
     float * sc = (float *) smem;                                   // [T]
     uint16_t * p16 = (uint16_t *)(sc + ((T + 3) & ~3));            // [T]
     float * part = (float *)(p16 + ((T + 7) & ~7));                // [4][D][8]
@@ -717,7 +781,7 @@ __global__ void __launch_bounds__(512) k_attention(const AttnArgs a) {
     #pragma unroll
     for (int c = 0; c < 8; c++) qf[c] = c < nch ? h2f(q[c * 32 + lane]) : 0.f;
     for (int t = warp; t < tcount; t += nwarp) {
-        const uint16_t * k = a.kc + (size_t) t * E + h * D;
+        const uint16_t * k = kcb + (size_t) t * E + h * D;
         float acc = 0.f;
         #pragma unroll
         for (int c = 0; c < 8; c++) if (c < nch) acc = ffma(h2f(k[c * 32 + lane]), qf[c], acc);
@@ -761,7 +825,7 @@ __global__ void __launch_bounds__(512) k_attention(const AttnArgs a) {
     const int g = tid / D, c = tid - g * D;
     if (g < 4) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const uint16_t * v = a.vc + h * D + c;
+        const uint16_t * v = vcb + h * D + c;
         const int lim = min(npT, tcount);
         for (int base = 8 * g; base < lim; base += 32) {
             #pragma unroll
@@ -784,7 +848,7 @@ __global__ void __launch_bounds__(512) k_attention(const AttnArgs a) {
         }
         const float t0 = fadd(vv[0], vv[4]), t1 = fadd(vv[1], vv[5]), t2 = fadd(vv[2], vv[6]), t3 = fadd(vv[3], vv[7]);
         double sumf = (double) fadd(fadd(t0, t1), fadd(t2, t3));
-        const uint16_t * v = a.vc + h * D + tid;
+        const uint16_t * v = vcb + h * D + tid;
         for (int t = npT; t < tcount; t++) sumf += (double) fmul(h2f(v[(size_t) t * E]), h2f(p16[t]));
         a.out[(size_t) n * E + h * D + tid] = (float) sumf;
     }
@@ -817,6 +881,7 @@ struct Attn128Args {
     float * part_scratch;         // [chunk][H][4][8][128]
     int n_ctx; float kq_scale;
     unsigned long long * trace;
+    const int2 * cols; size_t sess_stride;   // batched step (FUSE only): column n = (session, position); each column is an N = 1 step
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -833,11 +898,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     grid_dep_wait();
     if (threadIdx.x == 0) B200_TRACE(a.trace, 1);
     const int h = blockIdx.x >> 2, g = blockIdx.x & 3, ny = blockIdx.y, n = a.n0 + ny, E = a.E;
-    const int n_past = *a.n_past, T = n_past + a.N, tcount = n_past + n + 1, pos = n_past + n;
+    int T, tcount, pos;
+    uint16_t * kc = a.kc, * vc = a.vc;
+    if (a.cols) { const int2 c = a.cols[n]; pos = c.y; T = tcount = pos + 1; kc += (size_t) c.x * a.sess_stride; vc += (size_t) c.x * a.sess_stride; }
+    else { const int n_past = *a.n_past; T = n_past + a.N; tcount = n_past + n + 1; pos = n_past + n; }
     float * sc = (float *) smem;                                   // [T]
     uint16_t * p16 = (uint16_t *)(sc + ((T + 3) & ~3));            // [T]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint16_t * kc = a.kc, * vc = a.vc;
 
     // ---- phase 0: q (and, fused, the new k / v row) into shared memory
     if (FUSE) {
@@ -986,6 +1053,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
 
 // position counter kept on the device so a captured graph can be replayed for every token
 __global__ void k_advance(int * n_past, int by) { grid_dep_wait(); if (threadIdx.x == 0) *n_past += by; }
+// batched step: every listed session moves one position
+__global__ void k_advance_cols(int * n_past, const int2 * cols, int n) { grid_dep_wait(); if ((int) threadIdx.x < n) n_past[cols[threadIdx.x].x] += 1; }
 
 }  // namespace b200
 

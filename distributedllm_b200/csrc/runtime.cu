@@ -38,8 +38,13 @@ struct b200_slice {
     int device = 0, n_sm = 148;
     cudaStream_t stream = nullptr;
     int E = 0, H = 0, D = 0, FF = 0, L = 0, first_layer = 0, n_ctx = 512, wtype = 0;
-    int n_past = 0;
-    int * d_npast = nullptr;
+    // sessions: independent sequences sharing the weights, each with its own KV cache and position.
+    // Session 0 is the reference's single global context (tensor_processor.cpp:1491, 1992).
+    int n_sessions = 1, cur = 0;
+    std::vector<int> past;                 // n_past per session
+    int * d_npast = nullptr;               // [n_sessions], device copy (graph replays read it)
+    size_t sess_stride = 0;                // elements between two sessions' KV caches
+    int2 * d_cols = nullptr; const int2 * cols = nullptr;   // batched step: column -> (session, position)
     std::vector<LayerW> layers;
     std::vector<void *> allocs;
     uint16_t * kc = nullptr, * vc = nullptr, * q16 = nullptr;
@@ -56,7 +61,7 @@ struct b200_slice {
     bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true;
     bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
-    int opt_ns = 0, opt_qs = 0, opt_cta_per_sm = 0;
+    int opt_ns = 0, opt_qs = 0, opt_cta_per_sm = 0, opt_nc = 0;
     std::mutex mu;
     // per-kernel-class event timing (b200_slice_profile): class 0 qkv, 1 rope, 2 attention, 3 wo, 4 w13, 5 w2, 6 advance
     bool profiling = false; int cur_class = 0;
@@ -156,7 +161,17 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
 template <int WT, int G, int PRO, int EPI>
 static int launch_gemv_nc(b200_slice * s, const GemvArgs & a) {
     if (a.N == 1) return s->use_ring ? launch_gemv_t<WT, G, 1, PRO, EPI, true>(s, a) : launch_gemv_t<WT, G, 1, PRO, EPI, false>(s, a);
-    return s->use_ring ? launch_gemv_t<WT, G, 8, PRO, EPI, true>(s, a) : launch_gemv_t<WT, G, 8, PRO, EPI, false>(s, a);
+    if (!s->use_ring) return launch_gemv_t<WT, G, 8, PRO, EPI, false>(s, a);
+    // Columns per CTA.  A multi-column step is issue-bound (every column repeats the dp4a -> fadd -> fma chains), so it
+    // needs warps, not bytes: 8 columns per CTA amortise the nibble unpacking best, but a small batch (<= 8 columns)
+    // over a narrow matrix (wo / w2: 128-160 tiles) would then run ONE 4-warp CTA per SM.  Take the widest column
+    // group that still puts >= 3 CTAs on every SM; the extra column groups re-read the tile from L2, not from HBM
+    // (they are co-resident and walk the tiles in the same order).
+    const int want = 3 * s->n_sm, nt = a.W.n_tiles;
+    const int force = s->opt_nc;
+    if (force == 8 || (!force && nt * ((a.N + 7) / 8) >= want)) return launch_gemv_t<WT, G, 8, PRO, EPI, true>(s, a);
+    if (force == 4 || (!force && nt * ((a.N + 3) / 4) >= want)) return launch_gemv_t<WT, G, 4, PRO, EPI, true>(s, a);
+    return launch_gemv_t<WT, G, 2, PRO, EPI, true>(s, a);
 }
 
 template <int G, int PRO, int EPI>
@@ -195,6 +210,12 @@ static int launch_f16(b200_slice * s, GemvF16Args a) {
     return launch_simple(s, kern, dim3(gx, a.N, 1), dim3(256, 1, 1), smem, a);
 }
 
+static int launch_norm_quant(b200_slice * s, const float * x, int ldx, const float * norm_w, int N) {
+    NormQuantArgs q{x, ldx, norm_w, s->E, s->aq_x, s->da_x, s->nbqE};
+    if (s->wtype == kWT_Q4_0) return launch_simple(s, k_norm_quant<kWT_Q4_0>, dim3(N, 1, 1), dim3(256, 1, 1), 0, q);
+    return launch_simple(s, k_norm_quant<kWT_Q8_0>, dim3(N, 1, 1), dim3(256, 1, 1), 0, q);
+}
+
 // ---------------------------------------------------------------- fast-mode prefill (tcgen05), see fastgemm.cuh
 template <bool NORM>
 static int launch_prep(b200_slice * s, const float * x, int ldx, const float * norm_w, int K, int N) {
@@ -225,9 +246,12 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         // grid-barrier norm+quant epilogue: decode only (every CTA of wo / w2 must be co-resident: 1 tile per CTA)
         const bool fast = s->fast_prefill && N >= s->fast_min_tokens && s->wtype == kWT_Q4_0 && (Lw.qkv.n_tiles * Lw.qkv.TR) % 16 == 0 &&
                           (Lw.wo.n_tiles * Lw.wo.TR) % 16 == 0 && (Lw.w13.n_tiles * Lw.w13.TR) % 16 == 0;
-        const bool nq = s->use_nq && N == 1 && s->wtype != kWT_F16 && Lw.wo.n_tiles <= 256 && Lw.wo.n_tiles <= s->n_sm * 2;
+        const bool nq = s->use_nq && N == 1 && !s->cols && s->wtype != kWT_F16 && Lw.wo.n_tiles <= 256 && Lw.wo.n_tiles <= s->n_sm * 2;
         float * nxt = (il == s->L - 1) ? out : ((il & 1) ? s->xb : s->xa);
-        uint16_t * kc = s->kc + (size_t) il * s->n_ctx * E, * vc = s->vc + (size_t) il * s->n_ctx * E;
+        // cols mode (batched independent sequences): the kernels add session * sess_stride themselves
+        const size_t sess_off = s->cols ? 0 : (size_t) s->cur * s->sess_stride;
+        uint16_t * kc = s->kc + sess_off + (size_t) il * s->n_ctx * E, * vc = s->vc + sess_off + (size_t) il * s->n_ctx * E;
+        int * d_npast = s->d_npast + s->cur;
         int rc;
         s->cur_class = 0;
         if (s->wtype == kWT_F16) {
@@ -244,6 +268,11 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x;
             // layers after the first get their input already normalised + quantised by the previous w2's last CTA
             if (il > 0 && nq) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_STORE>(s, g))) return rc; }
+            else if (N > 1) {
+                // multi-token call: normalise + quantise every row ONCE instead of once per 32-row tile (k_norm_quant)
+                if ((rc = launch_norm_quant(s, cur, E, Lw.attn_norm, N))) return rc;
+                if ((rc = launch_gemv<1, PRO_PREQ, EPI_STORE>(s, g))) return rc;
+            }
             else                     { if ((rc = launch_gemv<1, PRO_NORM, EPI_STORE>(s, g))) return rc; }
         }
         if (s->skip_attention) {
@@ -253,20 +282,29 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             constexpr int kChunk = 32;
             const size_t asm_bytes = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + 64;
             Attn128Args aa{};
-            aa.qkv = s->qkv; aa.q16 = s->q16; aa.kc = kc; aa.vc = vc; aa.n_past = s->d_npast; aa.E = E; aa.H = H; aa.N = N;
+            aa.qkv = s->qkv; aa.q16 = s->q16; aa.kc = kc; aa.vc = vc; aa.n_past = d_npast; aa.E = E; aa.H = H; aa.N = N;
+            aa.cols = s->cols; aa.sess_stride = s->sess_stride;
             aa.cs = s->cs; aa.texp = s->texp; aa.out = s->att; aa.sc_scratch = s->sc_scratch; aa.part_scratch = s->part_scratch;
             aa.n_ctx = s->n_ctx; aa.kq_scale = 1.0f / sqrtf((float) E / (float) H);
             const bool preq = s->wtype != kWT_F16;
             const float dsc = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
             if (preq) { aa.aq_out = s->aq_att; aa.da_out = s->da_att; aa.out_nbq = s->nbqE; aa.out_dscale = dsc; }
-            if (N == 1) {
+            if (s->cols) {
+                // every column is an independent N = 1 step: the fused (RoPE + append) kernel, one cluster row per column
+                s->cur_class = 2;
+                for (int n0 = 0; n0 < N; n0 += kChunk) {
+                    aa.n0 = n0;
+                    const int cnt = N - n0 < kChunk ? N - n0 : kChunk;
+                    if ((rc = launch_simple(s, k_attn128<true>, dim3(4 * H, cnt, 1), dim3(256, 1, 1), asm_bytes, aa))) return rc;
+                }
+            } else if (N == 1) {
                 s->cur_class = 2;
                 aa.n0 = 0;
                 if (s->trace && s->trace_next < 512) { aa.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(2); s->trace_ctas.push_back(4 * H); }
                 if ((rc = launch_simple(s, k_attn128<true>, dim3(4 * H, 1, 1), dim3(256, 1, 1), asm_bytes, aa))) return rc;
             } else {
                 s->cur_class = 1;
-                RopeArgs ra{s->qkv, E, H, D, N, s->d_npast, s->cs, s->q16, kc, vc};
+                RopeArgs ra{s->qkv, E, H, D, N, d_npast, s->cs, s->q16, kc, vc, nullptr, 0};
                 if ((rc = launch_simple(s, k_rope_append, dim3((E / 2 + 255) / 256, N, 1), dim3(256, 1, 1), 0, ra))) return rc;
                 s->cur_class = 2;
                 for (int n0 = 0; n0 < N; n0 += kChunk) {
@@ -277,10 +315,10 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             }
         } else {
             s->cur_class = 1;
-            RopeArgs ra{s->qkv, E, H, D, N, s->d_npast, s->cs, s->q16, kc, vc};
+            RopeArgs ra{s->qkv, E, H, D, N, d_npast, s->cs, s->q16, kc, vc, s->cols, s->sess_stride};
             if ((rc = launch_simple(s, k_rope_append, dim3((E / 2 + 255) / 256, N, 1), dim3(256, 1, 1), 0, ra))) return rc;
             s->cur_class = 2;
-            AttnArgs aa{s->q16, kc, vc, s->d_npast, E, H, D, N, s->texp, s->att, 1.0f / sqrtf((float) E / (float) H)};
+            AttnArgs aa{s->q16, kc, vc, d_npast, E, H, D, N, s->texp, s->att, 1.0f / sqrtf((float) E / (float) H), s->cols, s->sess_stride};
             const size_t asm_bytes = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + (size_t) 4 * D * 8 * 4 + 64;
             if ((rc = launch_simple(s, k_attention, dim3(H, N, 1), dim3(512, 1, 1), asm_bytes, aa))) return rc;
         }
@@ -325,6 +363,10 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             g.N = N; g.out_rows = FF; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x;
             g.aq_out = s->aq_gate; g.da_out = s->da_gate; g.out_nbq = s->nbqF; g.out_dscale = dsc;
             if (nq) { if ((rc = launch_gemv<2, PRO_PREQ, EPI_GATEQ>(s, g))) return rc; }
+            else if (N > 1) {
+                if ((rc = launch_norm_quant(s, s->ffin, E, Lw.ffn_norm, N))) return rc;
+                if ((rc = launch_gemv<2, PRO_PREQ, EPI_GATEQ>(s, g))) return rc;
+            }
             else    { if ((rc = launch_gemv<2, PRO_NORM, EPI_GATEQ>(s, g))) return rc; }
             s->cur_class = 5;
             GemvArgs w{}; w.W = Lw.w2; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
@@ -346,7 +388,8 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
         s->cur_class = 6;
         prof_begin(s);
-        B200_CUDA(cudaLaunchKernelEx(&cfg, k_advance, s->d_npast, N));
+        if (s->cols) B200_CUDA(cudaLaunchKernelEx(&cfg, k_advance_cols, s->d_npast, s->cols, N));
+        else         B200_CUDA(cudaLaunchKernelEx(&cfg, k_advance, s->d_npast + s->cur, N));
         prof_end(s);
         s->launches++;
     }
@@ -355,7 +398,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
 
 // N = 1: replay a captured graph (host variant adds the H2D / D2H copies as graph nodes)
 static int run_decode_graph(b200_slice * s, const float * in, float * out, bool host) {
-    GraphKey key{in, out, (host ? 1 : 0) | (s->skip_attention ? 2 : 0)};
+    GraphKey key{in, out, (host ? 1 : 0) | (s->skip_attention ? 2 : 0) | (s->cur << 2)};
     auto it = s->graphs.find(key);
     const int per_step = (s->D == 128 ? 5 : 6) * s->L + (s->wtype == kWT_F16 ? 2 * s->L : 0) + 1;
     if (it == s->graphs.end()) {
@@ -386,11 +429,13 @@ static int run_decode_graph(b200_slice * s, const float * in, float * out, bool 
     return 0;
 }
 
-static int forward_locked(b200_slice * s, const float * in, int N, float * out, bool host) {
+static int forward_locked(b200_slice * s, const float * in, int N, float * out, bool host, int session = 0) {
     if (N <= 0) return fail(B200_EINVAL, "n_tokens must be positive (got %d)", N);
-    if (s->n_past + N > s->n_ctx)
-        return fail(B200_ECONTEXT, "context overflow: n_past %d + n_tokens %d > n_ctx %d", s->n_past, N, s->n_ctx);
+    if (session < 0 || session >= s->n_sessions) return fail(B200_EINVAL, "session %d outside [0, %d)", session, s->n_sessions);
+    if (s->past[session] + N > s->n_ctx)
+        return fail(B200_ECONTEXT, "context overflow: n_past %d + n_tokens %d > n_ctx %d", s->past[session], N, s->n_ctx);
     B200_CUDA(cudaSetDevice(s->device));
+    s->cur = session; s->cols = nullptr;
     B200_CUDA(cudaEventRecord(s->ev0, s->stream));
     int rc;
     if (host) {
@@ -413,7 +458,47 @@ static int forward_locked(b200_slice * s, const float * in, int N, float * out, 
         B200_CUDA(cudaEventRecord(s->ev1, s->stream));
     }
     s->timed = true;
-    s->n_past += N;
+    s->past[session] += N;
+    return 0;
+}
+
+// One token for each of B distinct sessions in a single pass: the weight matmuls see B columns (weights read once),
+// attention / RoPE / KV append run per column against that session's cache at that session's position.  Every column
+// is arithmetically the N = 1 step of its own sequence, so results are bit-identical to stepping the sessions one by one.
+static int batch_locked(b200_slice * s, const int * sessions, int B, const float * in, float * out, bool host) {
+    if (B <= 0 || B > s->n_sessions || B > s->n_ctx) return fail(B200_EINVAL, "batch of %d sequences with %d sessions", B, s->n_sessions);
+    std::vector<int2> cols(B);
+    std::vector<char> seen(s->n_sessions, 0);
+    for (int b = 0; b < B; b++) {
+        const int k = sessions[b];
+        if (k < 0 || k >= s->n_sessions) return fail(B200_EINVAL, "session %d outside [0, %d)", k, s->n_sessions);
+        if (seen[k]) return fail(B200_EINVAL, "session %d listed twice in one batched step", k);
+        seen[k] = 1;
+        if (s->past[k] + 1 > s->n_ctx) return fail(B200_ECONTEXT, "context overflow: session %d n_past %d + 1 > n_ctx %d", k, s->past[k], s->n_ctx);
+        cols[b] = make_int2(k, s->past[k]);
+    }
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaEventRecord(s->ev0, s->stream));
+    // pageable source: the driver stages it before returning, so the vector may go out of scope
+    B200_CUDA(cudaMemcpyAsync(s->d_cols, cols.data(), (size_t) B * sizeof(int2), cudaMemcpyHostToDevice, s->stream));
+    s->cur = 0; s->cols = s->d_cols;
+    int rc;
+    if (host) {
+        B200_CUDA(cudaMemcpyAsync(s->d_in, in, (size_t) B * s->E * 4, cudaMemcpyHostToDevice, s->stream));
+        rc = enqueue_layers(s, s->d_in, B, s->d_out);
+        s->cols = nullptr;
+        if (rc) return rc;
+        B200_CUDA(cudaEventRecord(s->ev1, s->stream));
+        B200_CUDA(cudaMemcpyAsync(out, s->d_out, (size_t) B * s->E * 4, cudaMemcpyDeviceToHost, s->stream));
+        B200_CUDA(cudaStreamSynchronize(s->stream));
+    } else {
+        rc = enqueue_layers(s, in, B, out);
+        s->cols = nullptr;
+        if (rc) return rc;
+        B200_CUDA(cudaEventRecord(s->ev1, s->stream));
+    }
+    s->timed = true;
+    for (int b = 0; b < B; b++) s->past[sessions[b]] += 1;
     return 0;
 }
 
@@ -558,11 +643,14 @@ static int load_locked(b200_slice * s, const char * path) {
     cudaFree(scratch);
 
     const size_t nE = (size_t) s->n_ctx * E;
-    if ((rc = dev_alloc(s, &s->kc, (size_t) s->L * nE)) || (rc = dev_alloc(s, &s->vc, (size_t) s->L * nE)) ||
+    s->sess_stride = (size_t) s->L * nE;
+    s->past.assign(s->n_sessions, 0);
+    if ((rc = dev_alloc(s, &s->kc, s->n_sessions * s->sess_stride)) || (rc = dev_alloc(s, &s->vc, s->n_sessions * s->sess_stride)) ||
+        (rc = dev_alloc(s, &s->d_cols, (size_t) s->n_ctx)) ||
         (rc = dev_alloc(s, &s->q16, nE)) || (rc = dev_alloc(s, &s->xa, nE)) || (rc = dev_alloc(s, &s->xb, nE)) ||
         (rc = dev_alloc(s, &s->qkv, 3 * nE)) || (rc = dev_alloc(s, &s->att, nE)) || (rc = dev_alloc(s, &s->ffin, nE)) ||
         (rc = dev_alloc(s, &s->gate, (size_t) s->n_ctx * FF)) || (rc = dev_alloc(s, &s->d_in, nE)) ||
-        (rc = dev_alloc(s, &s->d_out, nE)) || (rc = dev_alloc(s, &s->d_npast, 1)) ||
+        (rc = dev_alloc(s, &s->d_out, nE)) || (rc = dev_alloc(s, &s->d_npast, (size_t) s->n_sessions)) ||
         (rc = dev_alloc(s, &s->sc_scratch, (size_t) 32 * s->H * s->n_ctx)) || (rc = dev_alloc(s, &s->part_scratch, (size_t) 32 * s->H * 4096)))
         return rc;
     if ((rc = dev_alloc(s, &s->xh, (size_t) s->n_ctx * (FF > E ? FF : E) + 64))) return rc;
@@ -578,9 +666,9 @@ static int load_locked(b200_slice * s, const char * path) {
         B200_CUDA(cudaMemset(s->aq_att, 0, nq * s->nbqE * 128));  B200_CUDA(cudaMemset(s->da_att, 0, nq * s->nbqE * 16));
         B200_CUDA(cudaMemset(s->aq_gate, 0, nq * s->nbqF * 128)); B200_CUDA(cudaMemset(s->da_gate, 0, nq * s->nbqF * 16));
     }
-    B200_CUDA(cudaMemset(s->kc, 0, (size_t) s->L * nE * 2));
-    B200_CUDA(cudaMemset(s->vc, 0, (size_t) s->L * nE * 2));
-    B200_CUDA(cudaMemset(s->d_npast, 0, 4));
+    B200_CUDA(cudaMemset(s->kc, 0, s->n_sessions * s->sess_stride * 2));
+    B200_CUDA(cudaMemset(s->vc, 0, s->n_sessions * s->sess_stride * 2));
+    B200_CUDA(cudaMemset(s->d_npast, 0, 4 * (size_t) s->n_sessions));
     B200_CUDA(cudaMallocHost((void **) &s->h_in, (size_t) E * 4));
     B200_CUDA(cudaMallocHost((void **) &s->h_out, (size_t) E * 4));
     if ((rc = build_tables(s))) return rc;
@@ -621,8 +709,13 @@ const char * b200_last_error(void) { return b200::last_error_ref().c_str(); }
 const char * b200_version(void) { return "b200-slice 0.1 (sm_100a, exact mode)"; }
 
 int b200_slice_load(const char * path, int device, int n_ctx, b200_slice_t ** out) {
+    return b200_slice_load_ex(path, device, n_ctx, 1, out);
+}
+
+int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions, b200_slice_t ** out) {
     if (!path || !out) return fail(B200_EINVAL, "b200_slice_load: null argument");
     *out = nullptr;
+    if (n_sessions < 1 || n_sessions > 4096) return fail(B200_EINVAL, "n_sessions %d outside [1, 4096]", n_sessions);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(B200_ENODEV, "no CUDA device visible: the slice forward has no CPU fallback");
@@ -634,12 +727,13 @@ int b200_slice_load(const char * path, int device, int n_ctx, b200_slice_t ** ou
     b200_slice * s = new b200_slice();
     s->device = device; s->n_sm = prop.multiProcessorCount;
     s->n_ctx = n_ctx > 0 ? n_ctx : 512;               // vendor examples/common.h:28
+    s->n_sessions = n_sessions;
     s->use_ring  = env_int("B200_RING", 1) != 0;
     s->use_graph = env_int("B200_GRAPH", 1) != 0;
     s->use_pdl   = env_int("B200_PDL", 1) != 0;
     s->fast_prefill = env_int("B200_FAST_PREFILL", 0) != 0; s->fast_min_tokens = env_int("B200_FAST_MIN_TOKENS", 32);
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
-    s->opt_ns = env_int("B200_NS", 0); s->opt_qs = env_int("B200_QS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0);
+    s->opt_ns = env_int("B200_NS", 0); s->opt_qs = env_int("B200_QS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
     int rc = load_locked(s, path);
@@ -660,25 +754,25 @@ int b200_slice_clear(b200_slice_t * s) {
     B200_CUDA(cudaSetDevice(s->device));
     B200_CUDA(cudaMemsetAsync(s->d_npast, 0, 4, s->stream));
     B200_CUDA(cudaStreamSynchronize(s->stream));
-    s->n_past = 0;
+    s->past[0] = 0;
     return 0;
 }
 
 int b200_slice_rewind(b200_slice_t * s, int n_past) {
     if (!s) return fail(B200_EINVAL, "null handle");
     std::lock_guard<std::mutex> lk(s->mu);
-    if (n_past < 0 || n_past > s->n_past) return fail(B200_EINVAL, "rewind target %d outside [0, %d]", n_past, s->n_past);
+    if (n_past < 0 || n_past > s->past[0]) return fail(B200_EINVAL, "rewind target %d outside [0, %d]", n_past, s->past[0]);
     B200_CUDA(cudaSetDevice(s->device));
     B200_CUDA(cudaMemcpyAsync(s->d_npast, &n_past, 4, cudaMemcpyHostToDevice, s->stream));
     B200_CUDA(cudaStreamSynchronize(s->stream));
-    s->n_past = n_past;
+    s->past[0] = n_past;
     return 0;
 }
 
 int b200_slice_info(b200_slice_t * s, b200_slice_info_t * info) {
     if (!s || !info) return fail(B200_EINVAL, "null argument");
     info->n_embd = s->E; info->n_head = s->H; info->n_ff = s->FF; info->n_layer = s->L; info->first_layer = s->first_layer;
-    info->n_ctx = s->n_ctx; info->n_past = s->n_past; info->weight_type = s->wtype; info->device = s->device;
+    info->n_ctx = s->n_ctx; info->n_past = s->past[0]; info->weight_type = s->wtype; info->device = s->device;
     info->weight_bytes = s->weight_bytes; info->kv_bytes_per_pos = (int64_t) s->L * 2 * s->E * 2;
     return 0;
 }
@@ -693,6 +787,73 @@ int b200_slice_forward_device(b200_slice_t * s, const float * d_in, int n_tokens
     if (!s || !d_in || !d_out) return fail(B200_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(s->mu);
     int rc = forward_locked(s, d_in, n_tokens, d_out, false);
+    if (rc) return rc;
+    if (sync) B200_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+/* ---- sessions and batched steps (additive) ---- */
+int b200_session_count(b200_slice_t * s) { return s ? s->n_sessions : 0; }
+
+int b200_session_n_past(b200_slice_t * s, int session) {
+    if (!s || session < 0 || session >= s->n_sessions) return -1;
+    std::lock_guard<std::mutex> lk(s->mu);
+    return s->past[session];
+}
+
+int b200_session_clear(b200_slice_t * s, int session) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    if (session < -1 || session >= s->n_sessions) return fail(B200_EINVAL, "session %d outside [0, %d)", session, s->n_sessions);
+    std::lock_guard<std::mutex> lk(s->mu);
+    B200_CUDA(cudaSetDevice(s->device));
+    if (session < 0) {
+        B200_CUDA(cudaMemsetAsync(s->d_npast, 0, 4 * (size_t) s->n_sessions, s->stream));
+        std::fill(s->past.begin(), s->past.end(), 0);
+    } else {
+        B200_CUDA(cudaMemsetAsync(s->d_npast + session, 0, 4, s->stream));
+        s->past[session] = 0;
+    }
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int b200_session_rewind(b200_slice_t * s, int session, int n_past) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    if (session < 0 || session >= s->n_sessions) return fail(B200_EINVAL, "session %d outside [0, %d)", session, s->n_sessions);
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (n_past < 0 || n_past > s->past[session]) return fail(B200_EINVAL, "rewind target %d outside [0, %d]", n_past, s->past[session]);
+    B200_CUDA(cudaSetDevice(s->device));
+    B200_CUDA(cudaMemcpyAsync(s->d_npast + session, &n_past, 4, cudaMemcpyHostToDevice, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    s->past[session] = n_past;
+    return 0;
+}
+
+int b200_session_forward(b200_slice_t * s, int session, const float * in, int n_tokens, float * out) {
+    if (!s || !in || !out) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return forward_locked(s, in, n_tokens, out, true, session);
+}
+
+int b200_session_forward_device(b200_slice_t * s, int session, const float * d_in, int n_tokens, float * d_out, int sync) {
+    if (!s || !d_in || !d_out) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = forward_locked(s, d_in, n_tokens, d_out, false, session);
+    if (rc) return rc;
+    if (sync) B200_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int b200_batch_forward(b200_slice_t * s, const int * sessions, int n_seq, const float * in, float * out) {
+    if (!s || !sessions || !in || !out) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return batch_locked(s, sessions, n_seq, in, out, true);
+}
+
+int b200_batch_forward_device(b200_slice_t * s, const int * sessions, int n_seq, const float * d_in, float * d_out, int sync) {
+    if (!s || !sessions || !d_in || !d_out) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = batch_locked(s, sessions, n_seq, d_in, d_out, false);
     if (rc) return rc;
     if (sync) B200_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
@@ -893,12 +1054,13 @@ int b200_pipeline_init(b200_slice_t * s, int rank, int nranks, const void * id12
     return 0;
 }
 
-int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int ring) {
-    if (!s || !s->nccl_comm) return fail(B200_EINVAL, "pipeline not initialised");
+// recv <- rank-1, the slice's layers, send -> rank+1 (ring: the last rank hands its output back to rank 0).
+// sessions == nullptr: n_rows tokens of session `session`; else one token for each of the n_rows listed sessions.
+static int pipeline_step_locked(b200_slice * s, const float * d_in, int n_rows, int ring, int session, const int * sessions) {
     NcclApi & n = nccl();
-    std::lock_guard<std::mutex> lk(s->mu);
     B200_CUDA(cudaSetDevice(s->device));
-    const size_t count = (size_t) n_tokens * s->E;
+    if (n_rows <= 0 || n_rows > s->n_ctx) return fail(B200_EINVAL, "n_tokens %d outside [1, n_ctx]", n_rows);
+    const size_t count = (size_t) n_rows * s->E;
     const int r = s->pp_rank, W = s->pp_world;
     int rc;
     const float * in = d_in;
@@ -906,7 +1068,9 @@ int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int r
         if ((rc = n.Recv(s->d_in, count, kNcclFloat32, r - 1, s->nccl_comm, s->stream))) return nccl_fail("ncclRecv", rc);
         in = s->d_in;
     } else if (!in) return fail(B200_EINVAL, "rank 0 needs an input buffer");
-    if ((rc = forward_locked(s, in, n_tokens, s->d_out, false))) return rc;
+    if (sessions) rc = batch_locked(s, sessions, n_rows, in, s->d_out, false);
+    else          rc = forward_locked(s, in, n_rows, s->d_out, false, session);
+    if (rc) return rc;
     if (r < W - 1) {
         if ((rc = n.Send(s->d_out, count, kNcclFloat32, r + 1, s->nccl_comm, s->stream))) return nccl_fail("ncclSend", rc);
     } else if (ring && W > 1) {
@@ -918,6 +1082,25 @@ int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int r
     }
     s->launches += (r > 0) + (r < W - 1 || (ring && W > 1)) + (r == 0 && ring && W > 1);
     return 0;
+}
+
+int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int ring) {
+    if (!s || !s->nccl_comm) return fail(B200_EINVAL, "pipeline not initialised");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return pipeline_step_locked(s, d_in, n_tokens, ring, 0, nullptr);
+}
+
+int b200_pipeline_step_session(b200_slice_t * s, int session, const float * d_in, int n_tokens, int ring) {
+    if (!s || !s->nccl_comm) return fail(B200_EINVAL, "pipeline not initialised");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return pipeline_step_locked(s, d_in, n_tokens, ring, session, nullptr);
+}
+
+int b200_pipeline_step_batch(b200_slice_t * s, const int * sessions, int n_seq, const float * d_in, int ring) {
+    if (!s || !s->nccl_comm) return fail(B200_EINVAL, "pipeline not initialised");
+    if (!sessions) return fail(B200_EINVAL, "null session list");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return pipeline_step_locked(s, d_in, n_seq, ring, 0, sessions);
 }
 
 /* Device pointer of the pipeline's final activation on rank 0 (valid after a `ring` step), else dev_out. */

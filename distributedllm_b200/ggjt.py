@@ -462,3 +462,46 @@ def write_fast_q4_slice(path: str, shape: ModelShape, layer_from: int, layer_to:
                     left -= n
                     pos = 0
         return f.tell()
+
+
+def write_fast_f16_slice(path: str, shape: ModelShape, layer_from: int, layer_to: int, seed: int = 0) -> int:
+    """F16 twin of write_fast_q4_slice (BASELINE config 4: un-quantised 7B): each matrix is a window into a pool of
+    16 Mi fp16 values ~ N(0, 1/fan_in), one pool per fan-in.  Returns bytes written."""
+    vocab = default_vocab(shape.n_vocab)
+    hp = HParams(shape.n_vocab, shape.n_embd, shape.n_mult, shape.n_head, layer_to - layer_from + 1,
+                 shape.n_embd // shape.n_head, FTYPE_F16, layer_from)
+    e, ff = shape.n_embd, shape.n_ff
+    dims = {"attention.wq.weight": (e, e), "attention.wk.weight": (e, e), "attention.wv.weight": (e, e),
+            "attention.wo.weight": (e, e), "feed_forward.w1.weight": (ff, e), "feed_forward.w2.weight": (e, ff),
+            "feed_forward.w3.weight": (ff, e)}
+    n_pool = 1 << 24
+    pools = {}
+    for k in sorted({e, ff}):
+        rng = np.random.default_rng([seed, k, 79])
+        pools[k] = memoryview((rng.standard_normal(n_pool, dtype=np.float32) / np.float32(np.sqrt(k))).astype(np.float16)).cast("B")
+    pool_bytes = n_pool * 2
+    with open(path, "wb") as f:
+        _write_header(f, hp, vocab)
+        for layer in range(layer_from, layer_to + 1):
+            pre = "layers.%d." % layer
+            rng = np.random.default_rng([seed, layer, 80])
+            for nm in LAYER_TENSORS:
+                if nm.endswith("norm.weight"):
+                    w = (1.0 + 0.1 * rng.standard_normal(e)).astype(np.float32)
+                    _write_tensor(f, pre + nm, T_F32, (e,), w.tobytes())
+                    continue
+                rows, k = dims[nm]
+                nbytes = rows * k * 2
+                start = int(rng.integers(0, n_pool)) * 2
+                name = (pre + nm).encode("utf-8")
+                f.write(struct.pack("<III", 2, len(name), T_F16))
+                f.write(struct.pack("<2I", k, rows))
+                f.write(name)
+                f.write(b"\0" * ((-f.tell()) & 31))
+                left, pos = nbytes, start
+                while left:
+                    n = min(left, pool_bytes - pos)
+                    f.write(pools[k][pos:pos + n])
+                    left -= n
+                    pos = 0
+        return f.tell()

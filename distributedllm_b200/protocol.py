@@ -217,6 +217,12 @@ _SPEC = [
     ("ResponseWithError", "operation_failure", [("operation", str), ("error", str), ("description", str)]),
     ("RequestGreeting", "greeting_request", []),
     ("ResponseGreeting", "greeting_response", []),
+    # ---- additive (not in the reference's message set, same framing and field codecs) ----
+    # the tensor as ONE `bytes` field (raw native-endian f32, what `list` carries minus the per-float Python objects),
+    # plus `route`: a JSON list of "host:port" hops still to visit -- the node forwards its output to route[0] itself
+    # and relays the final reply, so the client sends once and receives once instead of once per node
+    ("RequestPropagateBytes", "propagate_bytes_request", [("axis0", int), ("axis1", int), ("data", bytes), ("route", str)]),
+    ("ResponsePropagateBytes", "tensor_bytes_response", [("axis0", int), ("axis1", int), ("data", bytes)]),
 ]
 
 for _cls_name, _wire, _fields in _SPEC:

@@ -75,6 +75,26 @@ int b200_slice_forward(b200_slice_t * s, const float * in, int n_tokens, float *
  * `sync` != 0.  Used when the activation already lives in HBM (chained slices, benchmarks). */
 int b200_slice_forward_device(b200_slice_t * s, const float * d_in, int n_tokens, float * d_out, int sync);
 
+/* ---- sessions and batched steps (additive: SURVEY 8f N3, BASELINE config 5) --------------------
+ * The reference holds ONE context per process (tensor_processor.cpp:1491, 1992), so a node serves one sequence at a
+ * time.  Here a slice may hold n_sessions independent contexts (own KV cache + own n_past) over the same weights.
+ * Session 0 is the context every b200_slice_* call above uses.  Each session behaves exactly like a reference slice
+ * of its own: results are bit-identical to a private slice fed the same tokens. */
+int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions, b200_slice_t ** out);
+int b200_session_count(b200_slice_t * s);
+int b200_session_n_past(b200_slice_t * s, int session);                      /* -1 on a bad argument */
+int b200_session_clear(b200_slice_t * s, int session);                       /* session -1 = every session */
+int b200_session_rewind(b200_slice_t * s, int session, int n_past);
+int b200_session_forward(b200_slice_t * s, int session, const float * in, int n_tokens, float * out);          /* host buffers */
+int b200_session_forward_device(b200_slice_t * s, int session, const float * d_in, int n_tokens, float * d_out, int sync);
+
+/* Throughput mode: ONE token for each of n_seq DISTINCT sessions in a single pass.  in / out are [n_seq][n_embd]; row b
+ * belongs to sessions[b] and is processed at that session's own position.  The weights are streamed once for the whole
+ * batch; every row's arithmetic is that of its own single-token step, so the result is bit-identical to calling
+ * b200_session_forward(sessions[b], row b, 1, ...) for each b.  A session listed twice -> B200_EINVAL. */
+int b200_batch_forward(b200_slice_t * s, const int * sessions, int n_seq, const float * in, float * out);      /* host buffers */
+int b200_batch_forward_device(b200_slice_t * s, const int * sessions, int n_seq, const float * d_in, float * d_out, int sync);
+
 /* Fast mode for prefill calls (n_tokens >= min_tokens): the Q4_0 weight matmuls run on the tcgen05 tensor cores with
  * the dequantisation fused in (csrc/fastgemm.cuh).  NOT bit-exact: operands are rounded to fp16 after the reference's
  * Q8_0 activation quantisation; deviation from exact mode is bounded in tests/test_gpu_fast_prefill.py.  Off by default
@@ -135,6 +155,10 @@ int b200_pipeline_init(b200_slice_t * s, int rank, int nranks, const void * id12
  * leaves the result in its dev_out buffer and, when `ring` != 0, also sends it to rank 0 (which
  * receives it into the buffer b200_pipeline_result() returns), closing the token loop. Asynchronous on the slice's stream. */
 int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int ring);
+/* The same hand-off for one session, and for a batched step (one token for each listed session: [n_seq][n_embd] moves
+ * between the slices).  Every rank passes the same session list. */
+int b200_pipeline_step_session(b200_slice_t * s, int session, const float * d_in, int n_tokens, int ring);
+int b200_pipeline_step_batch(b200_slice_t * s, const int * sessions, int n_seq, const float * d_in, int ring);
 /* Device pointer of the pipeline's final activation: on rank 0 after a ring step the last slice's output, else dev_out. */
 float * b200_pipeline_result(b200_slice_t * s);
 int b200_pipeline_destroy(b200_slice_t * s);

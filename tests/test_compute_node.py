@@ -118,3 +118,82 @@ def test_shape_mismatch_is_an_error(node, monkeypatch):
     monkeypatch.setattr(conn, "_get_response", lie)
     with pytest.raises(OperationFailedError):
         conn.propagate_forward([1.0, 2.0], (1, 2))
+
+
+# ---------------------------------------------------------------- additive wire format
+def _toy_node(tmp_path, name, k, b, loaded=True):
+    """A node with its own context (several per process) holding DummySlice(k, b)."""
+    ctx = RequestContext.default(str(tmp_path / name), names=[name])
+    srv = serve.make_server("127.0.0.1", 0, str(tmp_path / name), context=ctx)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    conn = Connection(("127.0.0.1", srv.server_address[1]))
+    if loaded:
+        conn.push_slice(io.BytesIO(bytes([k, b])), "toy", {"layer_from": 0, "layer_to": 0, "format": "test"})
+        conn.load_slice(name)
+    return srv, conn
+
+
+def test_binary_tensor_messages_round_trip():
+    import numpy as np
+    x = np.arange(6, dtype=np.float32) / 4
+    m = protocol.RequestPropagateBytes(2, 3, x.tobytes(), json.dumps(["10.0.0.2:9090"]))
+    name, body = protocol.decode_frame(m.encode()[4:])
+    assert name == "propagate_bytes_request" and protocol.restore_message(name, body) == m
+    # the field codecs are the reference's: a list-typed tensor of the same floats carries the same payload bytes
+    as_list = protocol.RequestPropagateForward(2, 3, x.tolist()).encode()
+    assert x.tobytes() in as_list and x.tobytes() in m.encode()
+    r = protocol.ResponsePropagateBytes(2, 3, x.tobytes())
+    name, body = protocol.decode_frame(r.encode()[4:])
+    assert protocol.restore_message(name, body) == r
+
+
+def test_binary_propagate_and_node_to_node_chain(tmp_path):
+    import numpy as np
+    nodes = [_toy_node(tmp_path, "n%d" % i, k, b) for i, (k, b) in enumerate([(2, 1), (3, 0), (1, 5)])]
+    try:
+        conns = [c for _, c in nodes]
+        x = np.array([0.5, -1.0, 2.0, 8.0], dtype=np.float32)
+        # star topology, list wire (the reference's) vs bytes wire: same numbers
+        want = x.tolist()
+        for c in conns:
+            want = c.propagate_forward(want, (1, 4))["values"]
+        got = x
+        for c in conns:
+            got = c.propagate_forward_bytes(got, (1, 4))
+        assert got.dtype == np.float32 and got.tolist() == want == [((2 * v + 1) * 3) + 5 for v in x.tolist()]
+        # chained: ONE request to the first node, which forwards along the route
+        route = ["127.0.0.1:%d" % s.server_address[1] for s, _ in nodes[1:]]
+        chained = conns[0].propagate_forward_bytes(x, (1, 4), route)
+        assert chained.tolist() == want
+        # client wrapper
+        from distributedllm_b200.client import DistributedLLM
+        llm = DistributedLLM.__new__(DistributedLLM)
+        llm.addresses = [("127.0.0.1", s.server_address[1]) for s, _ in nodes]
+        for wire in ("list", "bytes", "chain"):
+            llm.wire = wire
+            assert llm.propagate_tensor(x.tolist()) == want, wire
+    finally:
+        for s, _ in nodes:
+            s.shutdown()
+            s.server_close()
+
+
+def test_chain_failures_come_back_to_the_client(tmp_path):
+    import numpy as np
+    a = _toy_node(tmp_path, "a", 1, 1)
+    b = _toy_node(tmp_path, "b", 1, 1, loaded=False)        # no slice loaded on the second hop
+    try:
+        x = np.ones(3, dtype=np.float32)
+        with pytest.raises(OperationFailedError, match="slice_not_loaded"):
+            a[1].propagate_forward_bytes(x, (1, 3), ["127.0.0.1:%d" % b[0].server_address[1]])
+        with pytest.raises(OperationFailedError, match="chain_hop_failed"):
+            a[1].propagate_forward_bytes(x, (1, 3), ["127.0.0.1:1"])          # nothing listens there
+        # a tensor that is not a whole number of float32, and an unparsable hop
+        r = a[1]._get_response(protocol.RequestPropagateBytes(1, 3, b"\x00" * 5, "[]"))
+        assert r.get_message() == "operation_failure" and r.error == "neural_computation_error"
+        with pytest.raises(OperationFailedError, match="chain_hop_failed"):
+            a[1].propagate_forward_bytes(x, (1, 3), ["not-a-hop"])
+    finally:
+        for s, _ in (a, b):
+            s.shutdown()
+            s.server_close()

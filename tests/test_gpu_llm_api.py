@@ -143,6 +143,9 @@ def test_node_end_to_end_greedy_decode_matches_cpu_path(llm, tmp_path):
             want.append(t)
             toks = [t]
         assert ids == want
+        # additive binary wire format / chained route (one node here): same ids, tensors never become Python floats
+        for wire in ("bytes", "chain"):
+            assert DistributedLLM([addr], extra, wire=wire).generate_greedy("the the a in", max_steps=12) == want, wire
         ppl = model.perplexity("the the a in the")
         assert np.isfinite(ppl) and ppl > 1
     finally:

@@ -76,6 +76,17 @@ def test_launch_modes_agree(tmp_models, monkeypatch, pdl, graph, nq):
     assert bad == 0
 
 
+@pytest.mark.parametrize("nc", ["8", "4", "2"])
+@pytest.mark.parametrize("shape,wtype", [("tiny128", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q8_0)])
+def test_columns_per_cta_is_a_scheduling_choice(tmp_models, monkeypatch, nc, shape, wtype):
+    """Multi-token calls pick 8 / 4 / 2 columns per CTA from the matrix width and the batch; columns never interact."""
+    monkeypatch.setenv("B200_NC", nc)
+    sh = ggjt.SHAPES[shape]
+    path = tmp_models(shape, wtype, 0, 1)
+    bad, tot = _run_pair(path, [19, 8, 1, 3, 2], sh)
+    assert bad == 0
+
+
 def test_context_overflow_and_clear(tmp_models):
     from distributedllm_b200 import capi
 
