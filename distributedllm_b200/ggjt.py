@@ -505,3 +505,33 @@ def write_fast_f16_slice(path: str, shape: ModelShape, layer_from: int, layer_to
                     left -= n
                     pos = 0
         return f.tell()
+
+
+def write_fast_q4_extra(path: str, shape: ModelShape, seed: int = 0) -> int:
+    """Extra-layers file (tok_embeddings, norm, output -- all Q4_0 / f32) for the large shapes, from the same block
+    pool as write_fast_q4_slice.  Embedding rows come out with std ~ 1/sqrt(n_embd); the first RMSNorm rescales them."""
+    vocab = default_vocab(shape.n_vocab)
+    hp = HParams(shape.n_vocab, shape.n_embd, shape.n_mult, shape.n_head, 0, shape.n_embd // shape.n_head,
+                 FTYPE_Q4_0, NO_FIRST_LAYER)
+    e, v = shape.n_embd, shape.n_vocab
+    pool = memoryview(_fast_q4_pool(seed, e)).cast("B")
+    pool_bytes = _POOL_BLOCKS * 18
+    rng = np.random.default_rng([seed, 81])
+    with open(path, "wb") as f:
+        _write_header(f, hp, vocab)
+        for nm in ("tok_embeddings.weight", "norm.weight", "output.weight"):
+            if nm == "norm.weight":
+                _write_tensor(f, nm, T_F32, (e,), (1.0 + 0.1 * rng.standard_normal(e)).astype(np.float32).tobytes())
+                continue
+            name = nm.encode("utf-8")
+            f.write(struct.pack("<III", 2, len(name), T_Q4_0))
+            f.write(struct.pack("<2I", e, v))
+            f.write(name)
+            f.write(b"\0" * ((-f.tell()) & 31))
+            left, pos = v * e // QK * 18, int(rng.integers(0, _POOL_BLOCKS)) * 18
+            while left:
+                n = min(left, pool_bytes - pos)
+                f.write(pool[pos:pos + n])
+                left -= n
+                pos = 0
+        return f.tell()

@@ -23,7 +23,7 @@ a, b = layer_ranges(sh.n_layer, world)[rank]
 p = os.path.join(d, "s_%%d_%%d.bin" %% (a, b))
 if not os.path.exists(p):
     ggjt.write_synth_slice(p, sh, a, b, ggjt.T_Q4_0, seed=0)
-sl = capi.Slice(p, local, 64)
+sl = capi.Slice(p, local, 64, n_sessions=4)
 lib = capi.lib()
 idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
 if rank == 0:
@@ -37,7 +37,7 @@ rng = np.random.default_rng(21)
 ok = True
 if rank == 0:
     whole = os.path.join(d, "whole.bin"); ggjt.write_synth_slice(whole, sh, 0, sh.n_layer - 1, ggjt.T_Q4_0, seed=0)
-    ref = capi.Slice(whole, local, 64)
+    ref = capi.Slice(whole, local, 64, n_sessions=4)
 for n in (7, 1, 1, 5, 1):
     x = rng.standard_normal((n, sh.n_embd), dtype=np.float32)
     if rank == 0:
@@ -49,6 +49,30 @@ for n in (7, 1, 1, 5, 1):
         assert cudart.cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(lib.b200_pipeline_result(sl.handle)), C.c_size_t(out.nbytes), 2) == 0
         want = ref.forward(x)
         ok = ok and bool((out.view(np.uint32) == want.view(np.uint32)).all())
+# sessions through the pipeline: ragged prompts into sessions 1..3, then batched steps (one token per session)
+def fetch(n):
+    out = np.empty((n, sh.n_embd), np.float32)
+    assert cudart.cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(lib.b200_pipeline_result(sl.handle)), C.c_size_t(out.nbytes), 2) == 0
+    return out
+for k, n in ((1, 3), (2, 9), (3, 1)):
+    x = rng.standard_normal((n, sh.n_embd), dtype=np.float32)
+    if rank == 0:
+        assert cudart.cudaMemcpy(C.c_void_p(sl.dev_in), C.c_void_p(x.ctypes.data), C.c_size_t(x.nbytes), 1) == 0
+    capi.check(lib.b200_pipeline_step_session(sl.handle, k, C.c_void_p(sl.dev_in), n, 1))
+    sl.sync()
+    if rank == 0:
+        ok = ok and bool((fetch(n).view(np.uint32) == ref.session_forward(k, x).view(np.uint32)).all())
+ids = np.array([3, 1, 2], np.int32)
+for step in range(4):
+    x = rng.standard_normal((3, sh.n_embd), dtype=np.float32)
+    if rank == 0:
+        assert cudart.cudaMemcpy(C.c_void_p(sl.dev_in), C.c_void_p(x.ctypes.data), C.c_size_t(x.nbytes), 1) == 0
+    capi.check(lib.b200_pipeline_step_batch(sl.handle, C.c_void_p(ids.ctypes.data), 3, C.c_void_p(sl.dev_in), 1))
+    sl.sync()
+    if rank == 0:
+        got = fetch(3)
+        for j, k in enumerate(ids):
+            ok = ok and bool((got[j].view(np.uint32) == ref.session_forward(int(k), x[j:j + 1])[0].view(np.uint32)).all())
 dist.barrier()
 capi.check(lib.b200_pipeline_destroy(sl.handle))
 if rank == 0:
