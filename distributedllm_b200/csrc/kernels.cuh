@@ -147,7 +147,6 @@ struct GemvArgs {
     const uint16_t * tsilu;              // EPI_GATE*: fp16 SiLU table (65536 entries)
     int NS;                              // ring stages
     unsigned long long * trace;          // debug timeline (B200_TRACE), or null
-    int pdl_early;                       // trigger dependents at kernel start instead of after the last weight copy
     int pre_stages;                      // ring stages the producer may request before the prologue loads are issued
     int dbg_nomath;                      // debug: consume ring stages without computing (streaming-rate probe)
 };
@@ -240,7 +239,6 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
     if (RING && warp == kWPC) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
-            if (a.pdl_early) grid_dep_launch();
             int slot = 0, use = 0, issued = 0;
             for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
                 const uint8_t * src = a.W.data + (long long) tile * a.W.tile_bytes;
@@ -258,14 +256,18 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             }
             // This CTA has requested its last weight byte: let the NEXT kernel's CTAs become resident and
             // start THEIR weight stream now, so HBM never idles across the kernel boundary (depth-1 hand-off).
-            if (!a.pdl_early) grid_dep_launch();
+            // ORDERING GUARANTEE other kernels rely on (k_attn128's pre-wait KV prefetch): the trigger is never
+            // fired before this CTA's consumers have returned from griddepcontrol.wait (the gate below), i.e. not
+            // before the kernel BEFORE this one has completed.  By induction, whatever runs ahead of its own wait
+            // in the next kernel sees every kernel up to this one's predecessor finished.
+            if (issued <= a.pre_stages) mbar_wait(actbar + 1, 0);
+            grid_dep_launch();
             B200_TRACE(a.trace, 4);
         }
         return;
     }
 
     // ---------------------------------------------------------------------- consumer warps
-    if (!RING && tid == 0) grid_dep_launch();
     // static data first: the norm weights do not depend on the previous kernel, so their (possibly HBM) round trip
     // is issued before the dependency wait and kept in L2 for the next token
     float wn[32];
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
         }
     }
     grid_dep_wait();                                   // the input comes from the previous kernel
+    if (!RING && tid == 0) grid_dep_launch();          // (after the wait: same ordering guarantee as the ring producer)
     if (tid == 0) B200_TRACE(a.trace, 1);
 
     const int ncols = min(NC, a.N - col0);
@@ -882,11 +885,36 @@ struct Attn128Args {
     int n_ctx; float kq_scale;
     unsigned long long * trace;
     const int2 * cols; size_t sess_stride;   // batched step (FUSE only): column n = (session, position); each column is an N = 1 step
+    int pf_rows;                  // FUSE: rows of this CTA's K / V share staged in shared memory ahead of the dependency wait
 };
+
+constexpr int kAttnRow = 272;     // 256 B fp16 row + 16 B pad: the 8-thread phases of an LDS.128 never share a bank
+
+__device__ __forceinline__ void cp_async16(void * dst_smem, const void * src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait()           { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// address of the same shared-memory location in CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ uint32_t dsmem_addr(const void * local, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 template <bool FUSE>
@@ -894,9 +922,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(16) uint16_t q16s[128], k16s[128], v16s[128];
     __shared__ double redd[8]; __shared__ float redf[8];
+    __shared__ __align__(16) float partl[4 * 8 * 32];             // [source CTA j][slot l][channel of THIS CTA's 32]
     if (threadIdx.x == 0) { B200_TRACE(a.trace, 0); grid_dep_launch(); }
-    grid_dep_wait();
-    if (threadIdx.x == 0) B200_TRACE(a.trace, 1);
+    cluster_arrive_relaxed();                                      // "I am running": peers may write my shared memory after the matching wait
+    // FUSE (single-token steps): the kernel before this one is the qkv matmul, whose CTAs release their dependents only
+    // after their own dependency wait (see k_gemv).  So when this code runs, every kernel up to the one before qkv has
+    // finished: the position counter is final and all cache rows < pos are final.  Only the qkv row itself needs the wait.
+    if (!FUSE) grid_dep_wait();
     const int h = blockIdx.x >> 2, g = blockIdx.x & 3, ny = blockIdx.y, n = a.n0 + ny, E = a.E;
     int T, tcount, pos;
     uint16_t * kc = a.kc, * vc = a.vc;
@@ -905,6 +937,27 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     float * sc = (float *) smem;                                   // [T]
     uint16_t * p16 = (uint16_t *)(sc + ((T + 3) & ~3));            // [T]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // staged rows: local row i <-> position 32 (i >> 3) + 8 g + (i & 7), the positions this CTA scores and accumulates
+    uint8_t * Ks = smem + ((((size_t)((a.n_ctx + 3) & ~3) * 4 + (size_t)((a.n_ctx + 7) & ~7) * 2) + 15) & ~(size_t) 15);
+    uint8_t * Vs = Ks + (size_t) a.pf_rows * kAttnRow;
+    uint8_t * Vt = Vs + (size_t) a.pf_rows * kAttnRow;            // [32][64 B]: V rows of the double-precision tail, channels [32g, 32g+32)
+    const int npf = FUSE ? min(a.pf_rows, 8 * ((pos + 31) >> 5)) : 0;
+    if (FUSE) {
+        for (int idx = tid; idx < npf * 16; idx += 256) {
+            const int i = idx >> 4, ch = idx & 15, t = 32 * (i >> 3) + 8 * g + (i & 7);
+            if (t < pos) {
+                cp_async16(Ks + (size_t) i * kAttnRow + ch * 16, kc + (size_t) t * E + h * 128 + ch * 8);
+                cp_async16(Vs + (size_t) i * kAttnRow + ch * 16, vc + (size_t) t * E + h * 128 + ch * 8);
+            }
+        }
+        if (tid < 128) {
+            const int t = (T & ~31) + (tid >> 2), ch = tid & 3;
+            if (t < pos) cp_async16(Vt + (size_t)(tid >> 2) * 64 + ch * 16, vc + (size_t) t * E + h * 128 + 32 * g + ch * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        grid_dep_wait();
+    }
+    if (threadIdx.x == 0) B200_TRACE(a.trace, 1);
 
     // ---- phase 0: q (and, fused, the new k / v row) into shared memory
     if (FUSE) {
@@ -928,10 +981,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     } else {
         if (tid < 64) ((uint32_t *) q16s)[tid] = *(const uint32_t *)(a.q16 + (size_t) n * E + h * 128 + 2 * tid);
     }
+    if (FUSE) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     if (threadIdx.x == 0) B200_TRACE(a.trace, 2);
-    float * scg = a.sc_scratch + ((size_t) ny * a.H + h) * a.n_ctx;
+    cluster_wait();                                                // every CTA of the cluster has started
     // ---- phase 1: scores of the positions this CTA owns
     {
         const int sub = tid >> 2, ql = tid & 3;
@@ -944,7 +998,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
         for (int i = sub; i < nloc; i += 64) {
             const int t = 32 * (i >> 3) + 8 * g + (i & 7);
             const bool valid = t < tcount;
-            const uint16_t * krow = (FUSE && t == pos) ? k16s : kc + (size_t) t * E + h * 128;
+            const uint16_t * krow = (FUSE && t == pos) ? k16s : (i < npf ? (const uint16_t *)(Ks + (size_t) i * kAttnRow)
+                                                                          : kc + (size_t) t * E + h * 128);
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (valid) {
                 uint4 kv[4];
@@ -968,7 +1023,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
             }
             const float t0 = fadd(v8[0], v8[4]), t1 = fadd(v8[1], v8[5]), t2 = fadd(v8[2], v8[6]), t3 = fadd(v8[3], v8[7]);
             const float dot = fadd(fadd(t0, t1), fadd(t2, t3));
-            if (valid && ql == 0) scg[t] = fmul(dot, a.kq_scale);
+            if (valid && ql == 0) {
+                // scores meet in every CTA's shared memory (distributed shared memory), not in an L2 scratch
+                const float sv = fmul(dot, a.kq_scale);
+                #pragma unroll
+                for (int rnk = 0; rnk < 4; rnk++) dsmem_st(dsmem_addr(sc + t, rnk), sv);
+            }
         }
     }
     __syncthreads();
@@ -978,7 +1038,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
 
     // ---- phase 2: softmax over all t < tcount (every CTA, identical results)
     float mx = -INFINITY;
-    for (int t = tid; t < tcount; t += 256) { const float v = __ldcg(scg + t); sc[t] = v; mx = fmaxf(mx, v); }
+    for (int t = tid; t < tcount; t += 256) mx = fmaxf(mx, sc[t]);
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) redf[warp] = mx;
     __syncthreads();
@@ -1003,12 +1063,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     if (threadIdx.x == 0) B200_TRACE(a.trace, 6);
     // ---- phase 3: V.p partial sums of slots 8g..8g+7
     const int npT = T & ~31, lim = min(npT, tcount);
-    float * partg = a.part_scratch + (((size_t) ny * a.H + h) * 4) * 1024;
     if (tid < 128) {
         const int l = tid >> 4, cg = tid & 15;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int t = 8 * g + l; t < lim; t += 32) {
-            const uint16_t * vrow = (FUSE && t == pos) ? v16s : vc + (size_t) t * E + h * 128;
+            const int i = ((t >> 5) << 3) + l;
+            const uint16_t * vrow = (FUSE && t == pos) ? v16s : (i < npf ? (const uint16_t *)(Vs + (size_t) i * kAttnRow)
+                                                                          : vc + (size_t) t * E + h * 128);
             const uint4 vv = *(const uint4 *)(vrow + 8 * cg);
             const uint32_t u[4] = {vv.x, vv.y, vv.z, vv.w};
             const float p = h2f(p16[t]);
@@ -1018,9 +1079,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
                 acc[e] = ffma(h2f(vh), p, acc[e]);
             }
         }
-        float4 * dst = (float4 *)(partg + (size_t) g * 1024 + l * 128 + 8 * cg);
-        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        // channels 8cg..8cg+7 are finished by CTA cg >> 2: drop the slot partials straight into its shared memory
+        const uint32_t dst = dsmem_addr(partl + (g * 8 + l) * 32 + 8 * (cg & 3), cg >> 2);
+        dsmem_st4(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        dsmem_st4(dst + 16, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
     __syncthreads();
     cluster_sync_all();
@@ -1032,14 +1094,15 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
         float vv[8];
         #pragma unroll
         for (int l = 0; l < 8; l++) {
-            const float p0 = __ldcg(partg + 0 * 1024 + l * 128 + c), p1 = __ldcg(partg + 1 * 1024 + l * 128 + c);
-            const float p2 = __ldcg(partg + 2 * 1024 + l * 128 + c), p3 = __ldcg(partg + 3 * 1024 + l * 128 + c);
+            const float p0 = partl[(0 * 8 + l) * 32 + tid], p1 = partl[(1 * 8 + l) * 32 + tid];
+            const float p2 = partl[(2 * 8 + l) * 32 + tid], p3 = partl[(3 * 8 + l) * 32 + tid];
             vv[l] = fadd(fadd(p0, p2), fadd(p1, p3));
         }
         const float t0 = fadd(vv[0], vv[4]), t1 = fadd(vv[1], vv[5]), t2 = fadd(vv[2], vv[6]), t3 = fadd(vv[3], vv[7]);
         double sumf = (double) fadd(fadd(t0, t1), fadd(t2, t3));
         for (int t = npT; t < tcount; t++) {
-            const uint16_t vh = (FUSE && t == pos) ? v16s[c] : vc[(size_t) t * E + h * 128 + c];
+            const uint16_t vh = (FUSE && t == pos) ? v16s[c] : (FUSE ? ((const uint16_t *)(Vt + (size_t)(t - npT) * 64))[tid]
+                                                                     : vc[(size_t) t * E + h * 128 + c]);
             sumf += (double) fmul(h2f(vh), h2f(p16[t]));
         }
         const float ov = (float) sumf;

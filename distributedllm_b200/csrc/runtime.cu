@@ -131,7 +131,7 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[s->device & 15] = true;
     }
-    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pdl_early = env_int("B200_PDL_EARLY", 0); a.pre_stages = env_int("B200_PRE", 2);
+    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pre_stages = env_int("B200_PRE", 2);
     a.trace = nullptr;
     if (s->trace && s->trace_next < 512) { a.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(s->cur_class); }
     int per_sm = s->opt_cta_per_sm > 0 ? s->opt_cta_per_sm : (int)(kSmemLimit / (smem + 1024));
@@ -280,8 +280,13 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         } else if (D == 128) {
             // head size 128: cluster kernel; for N = 1 RoPE + KV append are fused into its prologue
             constexpr int kChunk = 32;
-            const size_t asm_bytes = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + 64;
+            // scores + probabilities, then (single-token kernels) the staged K / V rows: up to 128 local rows = 512 positions
+            const size_t sc_bytes = (((size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2) + 15) & ~(size_t) 15;
+            int pf_rows = 8 * ((s->n_ctx + 31) / 32);
+            if (pf_rows > 128) pf_rows = 128;
+            const size_t asm_plain = sc_bytes + 64, asm_bytes = sc_bytes + (size_t) 2 * pf_rows * kAttnRow + 32 * 64 + 64;
             Attn128Args aa{};
+            aa.pf_rows = pf_rows;
             aa.qkv = s->qkv; aa.q16 = s->q16; aa.kc = kc; aa.vc = vc; aa.n_past = d_npast; aa.E = E; aa.H = H; aa.N = N;
             aa.cols = s->cols; aa.sess_stride = s->sess_stride;
             aa.cs = s->cs; aa.texp = s->texp; aa.out = s->att; aa.sc_scratch = s->sc_scratch; aa.part_scratch = s->part_scratch;
@@ -310,7 +315,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
                 for (int n0 = 0; n0 < N; n0 += kChunk) {
                     aa.n0 = n0;
                     const int cnt = N - n0 < kChunk ? N - n0 : kChunk;
-                    if ((rc = launch_simple(s, k_attn128<false>, dim3(4 * H, cnt, 1), dim3(256, 1, 1), asm_bytes, aa))) return rc;
+                    if ((rc = launch_simple(s, k_attn128<false>, dim3(4 * H, cnt, 1), dim3(256, 1, 1), asm_plain, aa))) return rc;
                 }
             }
         } else {
