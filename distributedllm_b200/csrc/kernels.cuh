@@ -864,8 +864,8 @@ __global__ void __launch_bounds__(512) k_attention(const AttnArgs a) {
 //     8-lane vectors j = slot/8.  CTA g of the cluster owns vector j = g, i.e. positions
 //     t = 32k + 8g + l (l = 0..7): it computes THOSE scores and accumulates THOSE slots, so K and V
 //     are each read exactly once per step and 4x as many SMs pull on HBM/L2 per head.
-//   * scores and slot partials meet through a small global scratch (L2-resident) ordered by
-//     barrier.cluster release/acquire; every CTA then runs the (cheap) softmax redundantly and CTA g
+//   * scores and slot partials meet in the CTAs' shared memory (distributed shared memory stores, ordered by
+//     barrier.cluster release/acquire); every CTA then runs the (cheap) softmax redundantly and CTA g
 //     finishes channels [32g, 32g+32) with the fixed reduce tree and the double-precision tail.
 // FUSE (decode, N = 1): RoPE of q and k, fp16 rounding and the KV append of the new position are
 // done in the prologue from the f32 qkv row, removing the separate rope/append launch.
@@ -880,12 +880,11 @@ struct Attn128Args {
     const float2 * cs; const uint16_t * texp;
     float * out;                  // [N][E]
     int * aq_out; float * da_out; int out_nbq; float out_dscale;   // optional: Q8_0-quantised output for the wo matmul
-    float * sc_scratch;           // [chunk][H][n_ctx]
-    float * part_scratch;         // [chunk][H][4][8][128]
     int n_ctx; float kq_scale;
     unsigned long long * trace;
     const int2 * cols; size_t sess_stride;   // batched step (FUSE only): column n = (session, position); each column is an N = 1 step
     int pf_rows;                  // FUSE: rows of this CTA's K / V share staged in shared memory ahead of the dependency wait
+    int lut_smem;                 // FUSE: also stage the negative half of the exp table (64 KB) -- softmax arguments are <= 0
 };
 
 constexpr int kAttnRow = 272;     // 256 B fp16 row + 16 B pad: the 8-thread phases of an LDS.128 never share a bank
@@ -923,6 +922,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     __shared__ __align__(16) uint16_t q16s[128], k16s[128], v16s[128];
     __shared__ double redd[8]; __shared__ float redf[8];
     __shared__ __align__(16) float partl[4 * 8 * 32];             // [source CTA j][slot l][channel of THIS CTA's 32]
+    __shared__ __align__(8) uint64_t lutbar;
     if (threadIdx.x == 0) { B200_TRACE(a.trace, 0); grid_dep_launch(); }
     cluster_arrive_relaxed();                                      // "I am running": peers may write my shared memory after the matching wait
     // FUSE (single-token steps): the kernel before this one is the qkv matmul, whose CTAs release their dependents only
@@ -942,7 +942,17 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     uint8_t * Vs = Ks + (size_t) a.pf_rows * kAttnRow;
     uint8_t * Vt = Vs + (size_t) a.pf_rows * kAttnRow;            // [32][64 B]: V rows of the double-precision tail, channels [32g, 32g+32)
     const int npf = FUSE ? min(a.pf_rows, 8 * ((pos + 31) >> 5)) : 0;
+    uint16_t * luts = (uint16_t *)(Vt + 32 * 64);                 // [32768] exp table entries 0x8000..0xFFFF
+    float2 cs_pre = make_float2(0.f, 0.f);
     if (FUSE) {
+        if (a.lut_smem && tid == 0) {
+            mbar_init(&lutbar, 1);
+            mbar_fence_init();
+            mbar_arrive_expect_tx(&lutbar, 65536u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(luts)), "l"(a.texp + 32768), "r"(65536u), "r"(smem_u32(&lutbar)) : "memory");
+        }
+        if (tid < 64) cs_pre = a.cs[(size_t) pos * 64 + tid];      // host-built table: no dependency on the previous kernel
         for (int idx = tid; idx < npf * 16; idx += 256) {
             const int i = idx >> 4, ch = idx & 15, t = 32 * (i >> 3) + 8 * g + (i & 7);
             if (t < pos) {
@@ -963,7 +973,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     if (FUSE) {
         if (tid < 64) {
             const float * row = a.qkv + (size_t) n * 3 * E + h * 128;
-            const float2 cs = a.cs[(size_t) pos * 64 + tid];
+            const float2 cs = cs_pre;
             const float2 q = *(const float2 *)(row + 2 * tid);
             const float2 k = *(const float2 *)(row + E + 2 * tid);
             const float2 v = *(const float2 *)(row + 2 * E + 2 * tid);
@@ -1035,6 +1045,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     if (threadIdx.x == 0) B200_TRACE(a.trace, 4);
     cluster_sync_all();
     if (threadIdx.x == 0) B200_TRACE(a.trace, 5);
+    if (FUSE && a.lut_smem) mbar_wait(&lutbar, 0);
 
     // ---- phase 2: softmax over all t < tcount (every CTA, identical results)
     float mx = -INFINITY;
@@ -1047,7 +1058,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     for (int i = 1; i < 8; i++) mx = fmaxf(mx, redf[i]);
     double s = 0.0;
     for (int t = tid; t < tcount; t += 256) {
-        const float e = h2f(a.texp[f2h(fsub(sc[t], mx))]);
+        const uint16_t xi = f2h(fsub(sc[t], mx));
+        const float e = h2f((FUSE && a.lut_smem && xi >= 0x8000) ? luts[xi - 0x8000] : a.texp[xi]);
         sc[t] = e; s += (double) e;
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

@@ -51,7 +51,6 @@ struct b200_slice {
     float * xa = nullptr, * xb = nullptr, * qkv = nullptr, * att = nullptr, * ffin = nullptr, * gate = nullptr;
     float * d_in = nullptr, * d_out = nullptr, * h_in = nullptr, * h_out = nullptr;
     float2 * cs = nullptr; uint16_t * texp = nullptr, * tsilu = nullptr;
-    float * sc_scratch = nullptr, * part_scratch = nullptr;   // k_attn128 exchange buffers
     int * aq_att = nullptr, * aq_gate = nullptr; float * da_att = nullptr, * da_gate = nullptr;   // pre-quantised activations
     int nbqE = 0, nbqF = 0;
     int * aq_x = nullptr; float * da_x = nullptr; int * nq_counter = nullptr; double * nq_partial = nullptr;   // normalised+quantised layer input (last-CTA epilogue)
@@ -279,17 +278,18 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             // measurement aid: the matmul kernels of the step back to back, attention left out
         } else if (D == 128) {
             // head size 128: cluster kernel; for N = 1 RoPE + KV append are fused into its prologue
-            constexpr int kChunk = 32;
+            constexpr int kChunk = 1024;     // query tokens per launch (grid.y)
             // scores + probabilities, then (single-token kernels) the staged K / V rows: up to 128 local rows = 512 positions
             const size_t sc_bytes = (((size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2) + 15) & ~(size_t) 15;
             int pf_rows = 8 * ((s->n_ctx + 31) / 32);
             if (pf_rows > 128) pf_rows = 128;
             const size_t asm_plain = sc_bytes + 64, asm_bytes = sc_bytes + (size_t) 2 * pf_rows * kAttnRow + 32 * 64 + 64;
+            const size_t asm_lut = asm_bytes + 65536;            // + the exp table's negative half (single-token steps only)
             Attn128Args aa{};
             aa.pf_rows = pf_rows;
             aa.qkv = s->qkv; aa.q16 = s->q16; aa.kc = kc; aa.vc = vc; aa.n_past = d_npast; aa.E = E; aa.H = H; aa.N = N;
             aa.cols = s->cols; aa.sess_stride = s->sess_stride;
-            aa.cs = s->cs; aa.texp = s->texp; aa.out = s->att; aa.sc_scratch = s->sc_scratch; aa.part_scratch = s->part_scratch;
+            aa.cs = s->cs; aa.texp = s->texp; aa.out = s->att;
             aa.n_ctx = s->n_ctx; aa.kq_scale = 1.0f / sqrtf((float) E / (float) H);
             const bool preq = s->wtype != kWT_F16;
             const float dsc = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
@@ -306,7 +306,8 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
                 s->cur_class = 2;
                 aa.n0 = 0;
                 if (s->trace && s->trace_next < 512) { aa.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(2); s->trace_ctas.push_back(4 * H); }
-                if ((rc = launch_simple(s, k_attn128<true>, dim3(4 * H, 1, 1), dim3(256, 1, 1), asm_bytes, aa))) return rc;
+                aa.lut_smem = 1;
+                if ((rc = launch_simple(s, k_attn128<true>, dim3(4 * H, 1, 1), dim3(256, 1, 1), asm_lut, aa))) return rc;
             } else {
                 s->cur_class = 1;
                 RopeArgs ra{s->qkv, E, H, D, N, d_npast, s->cs, s->q16, kc, vc, nullptr, 0};
@@ -655,8 +656,7 @@ static int load_locked(b200_slice * s, const char * path) {
         (rc = dev_alloc(s, &s->q16, nE)) || (rc = dev_alloc(s, &s->xa, nE)) || (rc = dev_alloc(s, &s->xb, nE)) ||
         (rc = dev_alloc(s, &s->qkv, 3 * nE)) || (rc = dev_alloc(s, &s->att, nE)) || (rc = dev_alloc(s, &s->ffin, nE)) ||
         (rc = dev_alloc(s, &s->gate, (size_t) s->n_ctx * FF)) || (rc = dev_alloc(s, &s->d_in, nE)) ||
-        (rc = dev_alloc(s, &s->d_out, nE)) || (rc = dev_alloc(s, &s->d_npast, (size_t) s->n_sessions)) ||
-        (rc = dev_alloc(s, &s->sc_scratch, (size_t) 32 * s->H * s->n_ctx)) || (rc = dev_alloc(s, &s->part_scratch, (size_t) 32 * s->H * 4096)))
+        (rc = dev_alloc(s, &s->d_out, nE)) || (rc = dev_alloc(s, &s->d_npast, (size_t) s->n_sessions)))
         return rc;
     if ((rc = dev_alloc(s, &s->xh, (size_t) s->n_ctx * (FF > E ? FF : E) + 64))) return rc;
     if (s->wtype != kWT_F16) {

@@ -36,7 +36,11 @@ for i in range(first, min(n, first + 5)):
         pro = (d[:, 2] - d[:, 1]) / 1e3; main = (d[:, 3] - d[:, 2]) / 1e3
         q = lambda a: "%.2f / %.2f / %.2f / %.2f" % (a.min(), np.median(a), np.percentile(a, 90), a.max())
         print("%6s prologue %s | main %s | t1 spread %.2f" % (names[cls[i]], q(pro), q(main), (d[:, 1].max() - d[:, 1].min()) / 1e3))
-        if (d[:, 5] > 0).any():
+        if names[cls[i]] == "attn":
+            m = lambda a_, b_: np.median((d[:, a_] - d[:, b_]) / 1e3)
+            print("        median phases: wait->rope/q %.2f | scores %.2f | cluster sync %.2f | softmax %.2f | V.p %.2f (incl. sync) | finish %.2f"
+                  % (m(2, 1), m(4, 2), m(5, 4), m(6, 5), m(7, 6), m(3, 7)))
+        elif (d[:, 5] > 0).any():
             print("        prologue split: load+sum %s | reduce+scale %s | quant+bar %s" % (q((d[:, 5] - d[:, 1]) / 1e3), q((d[:, 6] - d[:, 5]) / 1e3), q((d[:, 2] - d[:, 6]) / 1e3)))
     else:
         tot = (d[:, 3] - d[:, 1]) / 1e3
