@@ -219,7 +219,9 @@ def run_b200(args):
     E = sh.n_embd
     a, b = layer_ranges(sh.n_layer, world)[rank]
     path = slice_file("7b", a, b)
+    t_load = time.perf_counter()
     sl = capi.Slice(path, local, N_CTX)
+    load_seconds = time.perf_counter() - t_load
     K, W = args.steps, args.warmup
     cycle = N_CTX - PREFILL
 
@@ -447,6 +449,7 @@ def run_b200(args):
                                                               "/".join(str(y - x + 1) for x, y in layer_ranges(32, world)), world),
                            "weights": "synthetic Q4_0 blocks (seed %d), reference slice-file format" % SEED,
                            "mode": "exact (bit-identical to the reference CPU path)",
+                           "slice_load_seconds": round(load_seconds, 3),
                            "parallelism": "pp%d (layer slices, NCCL send/recv hand-off)" % world if world > 1 else "pp1",
                            "l2": "no flush: each step streams %.2f GB of weights, 29x the 126 MB L2" % (W_all / 1e9),
                            "timing": "CUDA events on the slice's stream around %d steps; wall %.1f ms" % (K, wall_ms)},
