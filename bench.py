@@ -43,7 +43,8 @@ SEED = 0
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum per k_gemv launch, averaged over the 4 launches of a layer, from the
 # ncu --set full capture committed under profiles/ (None until that capture exists for the current kernels)
-NCU_TRAFFIC_PER_LAUNCH = 29.05e6    # profiles/r01_decode_kernels_ncu_full.md: (28.4 + 9.47 + 52.3 + 26.0) MB per layer / 4 launches; algorithmic 28.47e6
+NCU_TRAFFIC_PER_LAUNCH = 30.5e6     # profiles/r01_decode_kernels_ncu_full.md, two layers: reads (28.4 + 9.47 + 50.8 + 26.0) MB + writes (~7.4 MB of dirty
+                                    # activation / KV lines written back while w1|w3 streams) per layer / 4 launches; algorithmic 28.47e6 (no re-reads)
 
 
 def model_dir() -> str:
