@@ -427,7 +427,8 @@ static int run_decode_graph(b200_slice * s, const float * in, float * out, bool 
         e = cudaGraphInstantiate(&ge, g, 0);
         cudaGraphDestroy(g);
         if (e != cudaSuccess) return fail(B200_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-        if (s->graphs.size() >= 8) { for (auto & kv : s->graphs) cudaGraphExecDestroy(kv.second); s->graphs.clear(); }
+        if (s->graphs.size() >= 64)      // one graph per (buffers, session): enough for a node serving dozens of sessions
+            { for (auto & kv : s->graphs) cudaGraphExecDestroy(kv.second); s->graphs.clear(); }
         it = s->graphs.emplace(key, ge).first;
     }
     B200_CUDA(cudaGraphLaunch(it->second, s->stream));
