@@ -79,7 +79,7 @@ static PyObject * py_load_slice(PyObject *, PyObject * args) {
     b200_slice_t * s = nullptr;
     int rc;
     Py_BEGIN_ALLOW_THREADS
-    rc = b200_slice_load(path, env_int("B200_DEVICE", 0), env_int("B200_N_CTX", 0), &s);
+    rc = b200_slice_load_ex(path, env_int("B200_DEVICE", 0), env_int("B200_N_CTX", 0), env_int("B200_SESSIONS", 1), &s);
     Py_END_ALLOW_THREADS
     if (rc) return raise_b200("load_slice");
     std::lock_guard<std::mutex> lk(g_mu);
@@ -131,6 +131,63 @@ static PyObject * py_propagate_forward_buffer(PyObject *, PyObject * args) {
     const int rc = forward_vec(x, y);
     if (rc != 0) return raise_b200("propagate_forward");
     return PyBytes_FromStringAndSize((const char *) y.data(), (Py_ssize_t)(y.size() * sizeof(float)));
+}
+
+// ---- additive: several sequences on one node (B200_SESSIONS contexts over the same weights) ------------------
+// propagate_forward_session(session, float32 bytes-like) -> bytes        tokens of ONE session
+// propagate_forward_batch([sessions], float32 bytes-like) -> bytes       one token for EACH listed session, one pass
+// clear_session(session)  (-1 = all)
+static PyObject * py_propagate_forward_session(PyObject *, PyObject * args) {
+    int session; PyObject * values;
+    if (!PyArg_ParseTuple(args, "iO", &session, &values)) return nullptr;
+    if (!g_slice) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward_session: no slice loaded"); return nullptr; }
+    std::vector<float> x, y;
+    if (!list_to_floats(values, x)) return nullptr;
+    b200_slice_info_t info;
+    if (b200_slice_info(g_slice, &info)) return raise_b200("propagate_forward_session");
+    const int n_tokens = (int)(x.size() / (size_t) info.n_embd);
+    y.resize((size_t) n_tokens * info.n_embd);
+    int rc;
+    Py_BEGIN_ALLOW_THREADS
+    rc = b200_session_forward(g_slice, session, x.data(), n_tokens, y.data());
+    Py_END_ALLOW_THREADS
+    if (rc) return raise_b200("propagate_forward_session");
+    return PyBytes_FromStringAndSize((const char *) y.data(), (Py_ssize_t)(y.size() * sizeof(float)));
+}
+
+static PyObject * py_propagate_forward_batch(PyObject *, PyObject * args) {
+    PyObject * sessions, * values;
+    if (!PyArg_ParseTuple(args, "OO", &sessions, &values)) return nullptr;
+    if (!g_slice) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward_batch: no slice loaded"); return nullptr; }
+    if (!PyList_Check(sessions)) { PyErr_SetString(PyExc_TypeError, "propagate_forward_batch: sessions must be a list of int"); return nullptr; }
+    std::vector<int> ids((size_t) PyList_Size(sessions));
+    for (size_t i = 0; i < ids.size(); i++) {
+        const long v = PyLong_AsLong(PyList_GetItem(sessions, (Py_ssize_t) i));
+        if (v == -1 && PyErr_Occurred()) return nullptr;
+        ids[i] = (int) v;
+    }
+    std::vector<float> x, y;
+    if (!list_to_floats(values, x)) return nullptr;
+    b200_slice_info_t info;
+    if (b200_slice_info(g_slice, &info)) return raise_b200("propagate_forward_batch");
+    if (x.size() != ids.size() * (size_t) info.n_embd) {
+        PyErr_SetString(PyExc_ValueError, "propagate_forward_batch: need exactly one n_embd row per listed session");
+        return nullptr;
+    }
+    y.resize(x.size());
+    int rc;
+    Py_BEGIN_ALLOW_THREADS
+    rc = b200_batch_forward(g_slice, ids.data(), (int) ids.size(), x.data(), y.data());
+    Py_END_ALLOW_THREADS
+    if (rc) return raise_b200("propagate_forward_batch");
+    return PyBytes_FromStringAndSize((const char *) y.data(), (Py_ssize_t)(y.size() * sizeof(float)));
+}
+
+static PyObject * py_clear_session(PyObject *, PyObject * args) {
+    int session;
+    if (!PyArg_ParseTuple(args, "i", &session)) return nullptr;
+    if (g_slice && b200_session_clear(g_slice, session) != 0) return raise_b200("clear_session");
+    return PyLong_FromLong(0);
 }
 
 // ---- client side ---------------------------------------------------------------------------------------------
@@ -230,6 +287,9 @@ static PyMethodDef Methods[] = {
     {"prepare_embeddings", py_prepare_embeddings, METH_VARARGS, "Embed tokens for the first slice"},
     {"propagate_forward", py_propagate_forward, METH_VARARGS, "Propagate an embeddings vector through the layers of the slice"},
     {"propagate_forward_buffer", py_propagate_forward_buffer, METH_VARARGS, "Same, float32 bytes-like in, bytes out"},
+    {"propagate_forward_session", py_propagate_forward_session, METH_VARARGS, "(session, float32 buffer) -> bytes: tokens of one of B200_SESSIONS contexts"},
+    {"propagate_forward_batch", py_propagate_forward_batch, METH_VARARGS, "([sessions], float32 buffer) -> bytes: one token for each listed session in one pass"},
+    {"clear_session", py_clear_session, METH_VARARGS, "Clear one session's context (-1: all)"},
     {"get_logits", py_get_logits, METH_VARARGS, "Apply the output layers to embeddings to get logits"},
     {"get_next_token", py_get_next_token, METH_VARARGS, "Greedy next token"},
     {"decode_token", py_decode_token, METH_VARARGS, "Convert a token id to text"},

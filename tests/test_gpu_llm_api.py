@@ -184,3 +184,36 @@ def test_goldens_on_gpu(tmp_path):
             got = gpu.forward(data["%s/x%d" % (name, i)])
             assert (_bits(got) == _bits(data["%s/y%d" % (name, i)])).all(), (name, i)
         gpu.close()
+
+
+def test_llm_module_sessions(llm, tmp_models, monkeypatch):
+    """Additive llm functions for several sequences on one node; each session equals a private slice."""
+    from distributedllm_b200 import capi
+    sh = ggjt.SHAPES["tiny128"]
+    path = tmp_models("tiny128", ggjt.T_Q4_0, 0, 1, seed=31)
+    monkeypatch.setenv("B200_SESSIONS", "3")
+    monkeypatch.setenv("B200_N_CTX", "64")
+    llm.load_slice(path)
+    try:
+        rng = np.random.default_rng(5)
+        priv = [capi.Slice(path, 0, 64) for _ in range(3)]
+        for k, n in enumerate((4, 9, 1)):
+            x = rng.standard_normal((n, sh.n_embd), dtype=np.float32)
+            got = np.frombuffer(llm.propagate_forward_session(k, x), np.float32).reshape(n, -1)
+            assert (_bits(got) == _bits(priv[k].forward(x))).all()
+        x = rng.standard_normal((3, sh.n_embd), dtype=np.float32)
+        got = np.frombuffer(llm.propagate_forward_batch([2, 0, 1], x), np.float32).reshape(3, -1)
+        for j, k in enumerate((2, 0, 1)):
+            assert (_bits(got[j]) == _bits(priv[k].forward(x[j:j + 1])[0])).all()
+        # the reference-shaped call is session 0
+        y = rng.standard_normal((1, sh.n_embd), dtype=np.float32)
+        assert (_bits(np.array(llm.propagate_forward(y.ravel().tolist()), np.float32)) == _bits(priv[0].forward(y)[0])).all()
+        with pytest.raises(RuntimeError):
+            llm.propagate_forward_batch([0, 0], np.zeros((2, sh.n_embd), np.float32))
+        with pytest.raises(ValueError):
+            llm.propagate_forward_batch([0, 1], np.zeros((1, sh.n_embd), np.float32))
+        assert llm.clear_session(-1) == 0
+        for p in priv:
+            p.close()
+    finally:
+        llm.unload_slice()
