@@ -130,7 +130,7 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[s->device & 15] = true;
     }
-    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pre_stages = env_int("B200_PRE", 2);
+    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pre_stages = env_int("B200_PRE", 3);
     a.trace = nullptr;
     if (s->trace && s->trace_next < 512) { a.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(s->cur_class); }
     int per_sm = s->opt_cta_per_sm > 0 ? s->opt_cta_per_sm : (int)(kSmemLimit / (smem + 1024));
