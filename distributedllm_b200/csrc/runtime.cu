@@ -255,10 +255,8 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         s->cur_class = 0;
         if (s->wtype == kWT_F16) {
             GemvF16Args f{}; f.K = E; f.x = cur; f.ldx = E; f.norm_w = Lw.attn_norm; f.N = N; f.tsilu = s->tsilu;
-            f.rows = E; f.ldy = 3 * E;
+            f.rows = 3 * E; f.ldy = 3 * E;       // wq | wk | wv are packed back to back: one launch, one RMSNorm prologue
             f.W = Lw.f_q; f.y = s->qkv;         if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
-            f.W = Lw.f_k; f.y = s->qkv + E;     if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
-            f.W = Lw.f_v; f.y = s->qkv + 2 * E; if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
         } else if (fast) {
             if ((rc = launch_prep<true>(s, cur, E, Lw.attn_norm, E, N))) return rc;
             if ((rc = launch_fast_gemm<FG_STORE>(s, Lw.qkv, nullptr, 0, s->qkv, 3 * E, N, 3 * E))) return rc;
@@ -406,7 +404,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
 static int run_decode_graph(b200_slice * s, const float * in, float * out, bool host) {
     GraphKey key{in, out, (host ? 1 : 0) | (s->skip_attention ? 2 : 0) | (s->cur << 2)};
     auto it = s->graphs.find(key);
-    const int per_step = (s->D == 128 ? 5 : 6) * s->L + (s->wtype == kWT_F16 ? 2 * s->L : 0) + 1;
+    const int per_step = (s->D == 128 ? 5 : 6) * s->L + 1;
     if (it == s->graphs.end()) {
         const int64_t before = s->launches;
         cudaGraph_t g = nullptr;
@@ -546,12 +544,13 @@ static int pack_matrix(b200_slice * s, const GgjtFile & f, const GgjtTensor * co
     return 0;
 }
 
-static int pack_f16(b200_slice * s, const GgjtFile & f, const GgjtTensor & t, uint8_t * scratch, uint16_t ** out) {
+// `into`: pack into an existing buffer (wq | wk | wv share one, so the three matmuls are one launch over 3E rows)
+static int pack_f16(b200_slice * s, const GgjtFile & f, const GgjtTensor & t, uint8_t * scratch, uint16_t ** out, uint16_t * into = nullptr) {
     const int K = (int) t.ne[0], rows = (int) t.ne[1];
     const int nchunk = K / 32, nc8 = (nchunk + 7) / 8;
-    uint16_t * dst = nullptr;
-    int rc = dev_alloc(s, &dst, (size_t) rows * nc8 * 256 + 8);
-    if (rc) return rc;
+    uint16_t * dst = into;
+    int rc;
+    if (!dst && (rc = dev_alloc(s, &dst, (size_t) rows * nc8 * 256 + 8))) return rc;
     if ((rc = upload_raw(s, f, t, scratch))) return rc;
     k_repack_f16<<<s->n_sm * 8, 256, 0, s->stream>>>((const uint16_t *) scratch, dst, dst /*no tail: K%32==0*/, rows, K);
     B200_CUDA(cudaGetLastError());
@@ -630,7 +629,11 @@ static int load_locked(b200_slice * s, const char * path) {
             if (s->wtype == kWT_F16) {
                 const GgjtTensor * ts[7] = {&wq, &wk, &wv, &wo, &w1, &w2, &w3};
                 uint16_t ** dst[7] = {&Lw.f_q, &Lw.f_k, &Lw.f_v, &Lw.f_o, &Lw.f_1, &Lw.f_2, &Lw.f_3};
-                for (int k = 0; k < 7; k++) if ((rc = pack_f16(s, f, *ts[k], scratch, dst[k]))) { cudaFree(scratch); return rc; }
+                const size_t per = (size_t) E * ((E / 32 + 7) / 8) * 256;          // packed elements of one E x E matrix
+                uint16_t * qkv_buf = nullptr;
+                if ((rc = dev_alloc(s, &qkv_buf, 3 * per + 8))) { cudaFree(scratch); return rc; }
+                for (int k = 0; k < 7; k++)
+                    if ((rc = pack_f16(s, f, *ts[k], scratch, dst[k], k < 3 ? qkv_buf + k * per : nullptr))) { cudaFree(scratch); return rc; }
             } else {
                 const GgjtTensor * qkv[3] = {&wq, &wk, &wv};
                 const GgjtTensor * o1[1] = {&wo};
