@@ -102,3 +102,33 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
                 assert "liboracle" not in src and "libllmref" not in src, fn
+
+
+def test_fast_writers_produce_loadable_reference_format_files(tmp_path):
+    """The pool-based generators used for the large shapes (bench, full-size tests) write the same container the
+    reference's slice_model writes: header + first_layer, tensor directory, 32-byte aligned payloads of the right size."""
+    sh = ggjt.ModelShape(512, 256, 32, 4, 3)
+    q4, f16, ex = str(tmp_path / "q4.bin"), str(tmp_path / "f16.bin"), str(tmp_path / "extra.bin")
+    n = ggjt.write_fast_q4_slice(q4, sh, 1, 2, seed=7)
+    assert n == os.path.getsize(q4)
+    f = ggjt.read_file(q4, sliced=True)
+    assert f.hparams.n_layer == 2 and f.hparams.first_layer == 1 and len(f.tensors) == 18
+    w1 = f.tensors["layers.2.feed_forward.w1.weight"]
+    assert w1.ttype == ggjt.T_Q4_0 and tuple(w1.ne) == (sh.n_embd, sh.n_ff) and w1.offset % 32 == 0
+    assert w1.nbytes == sh.n_embd * sh.n_ff // 32 * 18
+    # deterministic, and any layer range of the same (shape, seed) carries the same bytes for a given layer
+    ggjt.write_fast_q4_slice(str(tmp_path / "q4b.bin"), sh, 2, 2, seed=7)
+    g = ggjt.read_file(str(tmp_path / "q4b.bin"), sliced=True)
+    a = open(q4, "rb").read()
+    b = open(str(tmp_path / "q4b.bin"), "rb").read()
+    t2 = g.tensors["layers.2.feed_forward.w1.weight"]
+    assert a[w1.offset:w1.offset + w1.nbytes] == b[t2.offset:t2.offset + t2.nbytes]
+    ggjt.write_fast_f16_slice(f16, sh, 0, 0, seed=7)
+    h = ggjt.read_file(f16, sliced=True)
+    wq = h.tensors["layers.0.attention.wq.weight"]
+    assert wq.ttype == ggjt.T_F16 and wq.nbytes == sh.n_embd * sh.n_embd * 2
+    vals = np.frombuffer(open(f16, "rb").read()[wq.offset:wq.offset + wq.nbytes], np.float16).astype(np.float32)
+    assert np.isfinite(vals).all() and 0.5 < vals.std() * np.sqrt(sh.n_embd) < 2.0
+    ggjt.write_fast_q4_extra(ex, sh, seed=7)
+    e = ggjt.read_file(ex, sliced=True)
+    assert list(e.tensors) == ["tok_embeddings.weight", "norm.weight", "output.weight"] and e.hparams.n_layer == 0
