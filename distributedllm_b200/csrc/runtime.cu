@@ -448,6 +448,9 @@ static int forward_locked(b200_slice * s, const float * in, int N, float * out, 
             memcpy(s->h_in, in, (size_t) s->E * 4);
             if ((rc = run_decode_graph(s, nullptr, nullptr, true))) return rc;
             B200_CUDA(cudaEventRecord(s->ev1, s->stream));
+            // a decoded token is ~1 ms of GPU work: poll for its completion (a blocking synchronize adds the wake-up
+            // latency of the driver's interrupt path to every token), fall back to blocking if it takes unusually long
+            for (int spin = 0; spin < 200000; spin++) if (cudaEventQuery(s->ev1) != cudaErrorNotReady) break;
             B200_CUDA(cudaStreamSynchronize(s->stream));
             memcpy(out, s->h_out, (size_t) s->E * 4);
         } else {
