@@ -103,3 +103,42 @@ def test_context_overflow_and_clear(tmp_models):
     y1 = s.forward(x)
     assert (_bits(y0) == _bits(y1)).all()
     s.close()
+
+
+def test_edge_cases_empty_ragged_and_full_context(tmp_models):
+    """Empty call, a ragged call length (not a multiple of the 8 / 4 / 2 column groups), filling the context to the last
+    position in one-token steps and in one call, rewinding: all as the reference behaves (tensor_processor.cpp:1523-1544
+    appends at n_past; the reference itself would write past its cache on overflow, we refuse)."""
+    from distributedllm_b200 import capi
+    from oracle import oracle
+    sh = ggjt.SHAPES["tiny128"]
+    path = tmp_models("tiny128", ggjt.T_Q4_0, 0, 0)
+    n_ctx = 40
+    gpu, ref = capi.Slice(path, 0, n_ctx), oracle.PortSlice(path, n_ctx)
+    with pytest.raises(capi.B200Error) as e:
+        gpu.forward(np.zeros((0, sh.n_embd), np.float32))
+    assert e.value.code == 1 and gpu.n_past == 0
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((13, sh.n_embd), dtype=np.float32)              # 13 = 8 + 4 + 1 columns
+    assert (_bits(gpu.forward(x)) == _bits(ref.forward(x))).all()
+    for _ in range(n_ctx - 13):                                            # up to the very last position
+        t = rng.standard_normal((1, sh.n_embd), dtype=np.float32)
+        assert (_bits(gpu.forward(t)) == _bits(ref.forward(t))).all()
+    assert gpu.n_past == n_ctx
+    with pytest.raises(capi.B200Error) as e:
+        gpu.forward(t)
+    assert e.value.code == 5 and gpu.n_past == n_ctx
+    # rewind to a previous position and replay: the cache below the rewind point is intact
+    gpu.rewind(13)
+    ref2 = oracle.PortSlice(path, n_ctx)
+    ref2.forward(x)
+    t = rng.standard_normal((5, sh.n_embd), dtype=np.float32)
+    assert (_bits(gpu.forward(t)) == _bits(ref2.forward(t))).all()
+    # the whole context in ONE call
+    gpu.clear_context()
+    ref3 = oracle.PortSlice(path, n_ctx)
+    full = rng.standard_normal((n_ctx, sh.n_embd), dtype=np.float32)
+    assert (_bits(gpu.forward(full)) == _bits(ref3.forward(full))).all()
+    for r in (ref, ref2, ref3):
+        r.close()
+    gpu.close()
