@@ -60,7 +60,7 @@ struct b200_slice {
     bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true;
     bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
-    int opt_ns = 0, opt_qs = 0, opt_cta_per_sm = 0, opt_nc = 0;
+    int opt_ns = 0, opt_cta_per_sm = 0, opt_nc = 0;
     std::mutex mu;
     // per-kernel-class event timing (b200_slice_profile): class 0 qkv, 1 rope, 2 attention, 3 wo, 4 w13, 5 w2, 6 advance
     bool profiling = false; int cur_class = 0;
@@ -745,7 +745,7 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->use_pdl   = env_int("B200_PDL", 1) != 0;
     s->fast_prefill = env_int("B200_FAST_PREFILL", 0) != 0; s->fast_min_tokens = env_int("B200_FAST_MIN_TOKENS", 32);
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
-    s->opt_ns = env_int("B200_NS", 0); s->opt_qs = env_int("B200_QS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
+    s->opt_ns = env_int("B200_NS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
     int rc = load_locked(s, path);
