@@ -180,6 +180,35 @@ def cpu_reference_run(path: str, n_embd: int, steps: int, warmup: int, prompt: i
     return (res, x0, xs, outs) if want_outputs else res
 
 
+def cpu_reference_chain(paths, n_embd: int, x0: np.ndarray, xq: np.ndarray):
+    """The reference's own multi-node data flow on the host: the activation goes through the slice files in order
+    (one reference slice loaded at a time, as one `llm` module holds one slice: tensor_processor.cpp:1992).  Returns
+    (timing dict, [prompt output, step outputs...]) -- the checker for the N-GPU pipeline and its cpu_baseline."""
+    from oracle import oracle
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    kind = "reference" if oracle.have_ref() else "port"
+    cores = min(16, avail) if kind == "reference" else avail
+    acts = [x0] + [xq[i:i + 1] for i in range(xq.shape[0])]
+    dt = 0.0
+    for p in paths:
+        sl = oracle.RefSlice(p, n_threads=cores, n_ctx=N_CTX) if kind == "reference" else oracle.PortSlice(p, N_CTX)
+        outs = [sl.forward(acts[0])]
+        for a in acts[1:]:
+            t0 = time.perf_counter()
+            outs.append(sl.forward(a))
+            dt += time.perf_counter() - t0
+        sl.close()
+        acts = outs
+    steps = xq.shape[0]
+    res = {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": 1e3 * dt / steps, "steps": steps,
+           "sample": "%d decode steps at positions %d..%d after a %d-token prompt through the %d slice files in sequence; "
+                     "%d threads" % (steps, x0.shape[0], x0.shape[0] + steps - 1, x0.shape[0], len(paths), cores)}
+    return res, acts
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -220,6 +249,9 @@ def run_b200(args):
     E = sh.n_embd
     a, b = layer_ranges(sh.n_layer, world)[rank]
     path = slice_file("7b", a, b)
+    t_init = time.perf_counter()
+    capi.check(capi.lib().b200_device_init(local))          # CUDA context creation (seconds on an 8-GPU box), not slice load
+    cuda_init_seconds = time.perf_counter() - t_init
     t_load = time.perf_counter()
     sl = capi.Slice(path, local, N_CTX)
     load_seconds = time.perf_counter() - t_load
@@ -297,6 +329,9 @@ def run_b200(args):
         dist.all_reduce(lt)
         launches = int(lt[0])
     value = K / (dev_ms / 1e3)
+    pos_timed = [PREFILL + (i % cycle) for i in range(W, W + K)]
+    timed_positions = ("%d..%d" % (pos_timed[0], pos_timed[-1]) if K <= cycle - (W % cycle) else
+                       "%d..%d cyclically (%d steps)" % (PREFILL, N_CTX - 1, K))
 
     # ---- e2e: the C ABI call with HOST buffers, one token per call (H2D + graph + D2H + sync)
     e2e = None
@@ -422,39 +457,105 @@ def run_b200(args):
     step_roof = {"algorithmic_bytes_per_step": b_step, "roofline_tokens_per_s_one_gpu": peak * 1e9 / b_step,
                  "frac_of_one_gpu": value / (peak * 1e9 / b_step), "frac_of_n_gpus": value / (world * peak * 1e9 / b_step)}
 
-    # ---- CPU baseline + parity spot check (rank 0, N=1 only)
+    # ---- tokens/s at the last position of the sequence (p = 511, T = 512: the longest KV read)
+    def step_any():
+        if world == 1:
+            sl.forward_device(sl.dev_in, 1, sl.dev_out)
+        else:
+            import ctypes as C
+            capi.check(capi.lib().b200_pipeline_step(sl.handle, C.c_void_p(sl.dev_in), 1, 1))
+
+    if sl.n_past > N_CTX - 1:
+        sl.rewind(N_CTX - 1)
+    while sl.n_past < N_CTX - 1:
+        step_any()                       # fill the cache up to position 510 (values do not matter for timing)
+    barrier()
+    p511 = []
+    for i in range(3 + 16):
+        sl.mark(0)
+        step_any()
+        sl.mark(1)
+        barrier()
+        if i >= 3:
+            p511.append(sl.mark_elapsed_ms())
+        sl.rewind(N_CTX - 1)
+    p511_ms = float(statistics.median(p511))
+    if dist is not None:
+        import torch
+        t = torch.tensor([p511_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        p511_ms = float(t[0])
+    b511 = W_all + kv_pos * N_CTX
+    at_p511 = {"tokens_per_s": 1e3 / p511_ms, "ms_per_step": p511_ms, "algorithmic_bytes": b511,
+               "frac_of_one_gpu": (1e3 / p511_ms) / (peak * 1e9 / b511),
+               "how": "median of 16 single steps at position 511, one CUDA-event pair each on the slice's stream, max over ranks"}
+
+    # ---- CPU baseline + parity against the compiled reference, EVERY N: rank 0 runs the reference over the N slice
+    # files in sequence (the reference's own multi-node data flow, cli_api/common.py:148-154) on a 16-token prompt +
+    # 16 decode steps; the GPU pipeline then runs the same tokens and the ring result is compared bit for bit.
     cpu = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if not args.no_cpu:
+        NPAR, PROMPT = 16, 16
+        x0 = synth_inputs(PROMPT, E, 1)
+        xq = synth_inputs(NPAR + 1, E, 2)
+        want = None
+        if rank == 0:
+            try:
+                if world == 1:
+                    r, x0, xq, outs = cpu_reference_run(path, E, NPAR, 1, prompt=PROMPT, want_outputs=True)
+                    want = [None] + outs                       # the prompt's output is not compared at N=1 (as round 1)
+                else:
+                    r, want = cpu_reference_chain([slice_file("7b", x, y) for x, y in layer_ranges(sh.n_layer, world)],
+                                                  E, x0, xq)
+                cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as ex:  # the bench line must still print
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+        barrier()
         try:
-            r, x0, xq, outs = cpu_reference_run(path, E, 16, 1, prompt=16, want_outputs=True)
-            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             sl.clear_context()
-            sl.forward(x0)
+            barrier()
             bad = tot = 0
-            for i, o in enumerate(outs):
-                g = sl.forward(xq[i:i + 1])
-                bad += int((g.view(np.uint32) != np.ascontiguousarray(o).view(np.uint32)).sum())
-                tot += g.size
-            parity = {"checked_floats": tot, "mismatching_floats": bad, "against": r["kind"]}
-        except Exception as ex:  # the bench line must still print
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+            got_all = []
+            for j, x in enumerate([x0] + [xq[i:i + 1] for i in range(xq.shape[0])]):
+                if world == 1:
+                    g = sl.forward(x)
+                else:
+                    import ctypes as C
+                    if rank == 0:
+                        _h2d(sl, x)
+                    capi.check(capi.lib().b200_pipeline_step(sl.handle, C.c_void_p(sl.dev_in), x.shape[0], 1))
+                    g = np.empty_like(x)
+                    if rank == 0:
+                        _d2h(sl, g)
+                if rank == 0 and want is not None and want[j] is not None:
+                    bad += int((g.view(np.uint32) != np.ascontiguousarray(want[j]).view(np.uint32)).sum())
+                    tot += g.size
+            if rank == 0 and want is not None:
+                parity = {"checked_floats": tot, "mismatching_floats": bad, "against": cpu.get("kind"),
+                          "what": "hidden states of the full 32-layer model through %d slice(s): %s%d decode steps, "
+                                  "bit patterns compared" % (world, "a %d-token prompt call + " % PROMPT if world > 1 else "", NPAR + 1)}
+        except Exception as ex:
+            parity = {"error": repr(ex)}
+        barrier()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "q4_0*q8_0->f32", "data": "synthetic",
                 "config": {"workload": "LLaMA-7B Q4_0 (BASELINE.json configs[%d]): %d slice(s) x %s layers on %dxB200, "
-                                       "n_ctx=512 batch=1, one decoded token per step at positions 256..511 after a "
-                                       "256-token prefill" % (1 if world == 1 else 2, world,
-                                                              "/".join(str(y - x + 1) for x, y in layer_ranges(32, world)), world),
+                                       "n_ctx=512 batch=1, one decoded token per step after a 256-token prefill; timed steps at "
+                                       "positions %s" % (1 if world == 1 else 2, world,
+                                                          "/".join(str(y - x + 1) for x, y in layer_ranges(32, world)), world,
+                                                          timed_positions),
                            "weights": "synthetic Q4_0 blocks (seed %d), reference slice-file format" % SEED,
                            "mode": "exact (bit-identical to the reference CPU path)",
-                           "slice_load_seconds": round(load_seconds, 3),
+                           "slice_load_seconds": round(load_seconds, 3), "cuda_init_seconds": round(cuda_init_seconds, 3),
                            "parallelism": "pp%d (layer slices, NCCL send/recv hand-off)" % world if world > 1 else "pp1",
                            "l2": "no flush: each step streams %.2f GB of weights, 29x the 126 MB L2" % (W_all / 1e9),
                            "timing": "CUDA events on the slice's stream around %d steps; wall %.1f ms" % (K, wall_ms)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "step_roofline": step_roof,
+                "tokens_per_s_at_p511": at_p511["tokens_per_s"], "at_p511": at_p511,
                 "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -487,9 +588,11 @@ def _h2d(sl, x: np.ndarray):
 
 
 def _d2h(sl, out: np.ndarray):
+    """Read the step's result back to the host: the slice's own output on one GPU, and on rank 0 of a ring pipeline the
+    LAST slice's output that the ring returned (b200_pipeline_result), i.e. the model's hidden state, not rank 0's."""
     import ctypes as C
     sl.sync()
-    rc = _cudart().cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(sl.dev_out), C.c_size_t(out.nbytes), 2)
+    rc = _cudart().cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(sl.pipeline_result), C.c_size_t(out.nbytes), 2)
     assert rc == 0, rc
 
 

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libb200slice.so")
 LLM = os.path.join(HERE, "llm" + sysconfig.get_config_var("EXT_SUFFIX"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["runtime.cu", "pipeline.cu", "extra.cu", "fastgemm.cu"]
+CU_SOURCES = ["runtime.cu"]          # one translation unit: kernels.cuh / fastgemm.cuh are headers of it
 
 
 def _newer(target: str, deps) -> bool:

@@ -74,6 +74,9 @@ def lib() -> C.CDLL:
         L.b200_slice_dev_in.restype = vp
         L.b200_slice_dev_out.argtypes = [vp]
         L.b200_slice_dev_out.restype = vp
+        L.b200_pipeline_result.argtypes = [vp]
+        L.b200_pipeline_result.restype = vp
+        L.b200_device_init.argtypes = [ci]
         for name, args in (("b200_pipeline_unique_id", [vp]), ("b200_pipeline_init", [vp, ci, ci, vp]),
                            ("b200_pipeline_step", [vp, vp, ci, ci]),
                            ("b200_pipeline_step_session", [vp, ci, vp, ci, ci]), ("b200_pipeline_step_batch", [vp, vp, ci, vp, ci]), ("b200_pipeline_destroy", [vp]),
@@ -180,6 +183,11 @@ class Slice:
     @property
     def dev_out(self) -> int:
         return lib().b200_slice_dev_out(self._h)
+
+    @property
+    def pipeline_result(self) -> int:
+        """Device pointer of the step's final activation: dev_out, or on rank 0 of a ring pipeline the last slice's output."""
+        return lib().b200_pipeline_result(self._h)
 
     def set_fast_prefill(self, on: bool, min_tokens: int = 0) -> None:
         check(lib().b200_slice_set_fast_prefill(self._h, int(on), min_tokens))

@@ -123,9 +123,30 @@ def handle_propagate_forward(ctx, message):
     return protocol.ResponsePropagateForward(axis0, axis1, out.values)
 
 
+MAX_ROUTE_HOPS = 64
+
+
 def parse_hop(hop: str):
+    if not isinstance(hop, str):
+        raise ValueError("hop must be 'host:port'")
     host, _, port = hop.rpartition(":")
+    if not host or not port.isdigit() or not 0 < int(port) < 65536:
+        raise ValueError("hop %r is not 'host:port'" % (hop,))
     return host, int(port)
+
+
+def check_route(ctx, hops):
+    """A route is client-supplied: bound its length, validate every hop's format BEFORE running the forward, refuse
+    loops back to this node, and -- when the node was started with a peer list -- hops outside it."""
+    if not isinstance(hops, list) or len(hops) > MAX_ROUTE_HOPS:
+        raise ValueError("route must be a list of at most %d hops" % MAX_ROUTE_HOPS)
+    peers, me = set(getattr(ctx, "peers", ()) or ()), set(getattr(ctx, "self_addresses", ()) or ())
+    for hop in hops:
+        parse_hop(hop)
+        if hop in me:
+            raise ValueError("route loops back to this node (%s)" % hop)
+        if peers and hop not in peers:
+            raise ValueError("hop %s is not in this node's peer list" % hop)
 
 
 @route("propagate_bytes_request")
@@ -133,6 +154,11 @@ def handle_propagate_bytes(ctx, message):
     import numpy as np
     if len(message.data) % 4:
         return _failure(message, "neural_computation_error", "tensor is not a whole number of float32")
+    try:
+        hops = json.loads(message.route) if message.route else []
+        check_route(ctx, hops)
+    except ValueError as e:
+        return _failure(message, "chain_hop_failed", "bad route: %s" % e)
     tensor = Tensor((message.axis0, message.axis1), np.frombuffer(message.data, dtype=np.float32))
     try:
         out = ctx.slice_container.forward(tensor)
@@ -141,10 +167,6 @@ def handle_propagate_bytes(ctx, message):
     except SliceNotLoadedError:
         return _failure(message, "slice_not_loaded")
     data = np.ascontiguousarray(out.values, dtype=np.float32).tobytes()
-    try:
-        hops = json.loads(message.route) if message.route else []
-    except ValueError:
-        return _failure(message, "chain_hop_failed", "unparsable route")
     if not hops:
         return protocol.ResponsePropagateBytes(out.shape[0], out.shape[1], data)
     # hand the activation to the next node ourselves and relay whatever comes back (a tensor or a failure)

@@ -20,8 +20,9 @@ def restore_registry(ctx: RequestContext, uploads_dir: str) -> None:
     if os.path.isfile(path):
         with open(path) as f:
             ctx.registry.load_state_dict(json.loads(f.read()))
-    else:
-        ctx.registry.root = uploads_dir
+    # the directory the node was STARTED with wins over the root spelled in a restored registry_data.json ("uploads" vs
+    # "./uploads" vs an absolute path, or a registry written elsewhere): locations are derived from the root
+    ctx.registry.root = uploads_dir
 
 
 class _Handler(socketserver.BaseRequestHandler):

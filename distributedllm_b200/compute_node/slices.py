@@ -63,13 +63,34 @@ class DummySlice(ModelSlice):
         return Tensor(tensor.shape, [self.k * v + self.b for v in tensor.values])
 
 
+LOAD_OPTION_KEYS = ("n_ctx", "device", "n_sessions")
+
+
+def load_options(metadata) -> dict:
+    """Per-slice load options carried by the slice's upload metadata: context length, GPU ordinal and
+    session count -- the knobs the reference hard-codes at tensor_processor.cpp:1997-2006.  Accepted at the top level
+    of the metadata JSON or under a "b200" sub-object; anything else in the metadata is ignored here."""
+    opts = {}
+    for src in (metadata or {}, (metadata or {}).get("b200") or {}):
+        for k in LOAD_OPTION_KEYS:
+            v = src.get(k) if isinstance(src, dict) else None
+            if v is None:
+                continue
+            v = int(v)
+            if v < 0 or (k != "device" and v == 0):
+                raise ValueError("slice metadata: %s must be positive (got %r)" % (k, v))
+            opts[k] = v
+    return opts
+
+
 class GGMLSlice(ModelSlice):
     """A reference-format slice file resident on the GPU."""
 
-    def __init__(self, file_path: str):
+    def __init__(self, file_path: str, **options):
         self.path = file_path
+        self.options = {k: int(v) for k, v in options.items() if k in LOAD_OPTION_KEYS and v is not None}
         self.llm = import_llm()
-        self.llm.load_slice(self.path)
+        self.llm.load_slice(self.path, **self.options)     # keyword extras are additive; llm.load_slice(path) still works
 
     def __call__(self, tensor: Tensor) -> Tensor:
         if hasattr(tensor.values, "dtype"):
@@ -103,7 +124,7 @@ class SliceContainer:
                 data = f.read()
             self.slice = DummySlice(data[0], data[1])
         else:
-            self.slice = GGMLSlice(slice_path)
+            self.slice = GGMLSlice(slice_path, **load_options(metadata))
 
     def forward(self, tensor: Tensor) -> Tensor:
         if self.slice is None:

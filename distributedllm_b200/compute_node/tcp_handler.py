@@ -25,12 +25,15 @@ class RequestContext:
     manager: UploadManager
     name_gen: FunkyNameGenerator
     slice_container: SliceContainer
+    uploads_dir: str = "uploads"          # what the singleton is keyed on (NOT registry.root, which a restore rewrites)
+    peers: tuple = ()                     # "host:port" of nodes this one may chain to (empty: any, see routes.py)
+    self_addresses: tuple = ()            # this node's own "host:port" spellings: a route may not loop back
 
     @classmethod
     def default(cls, uploads_dir="uploads", names=None):
         fs = MemoryFS()
         registry = UploadRegistry(uploads_dir)
-        return cls(registry, UploadManager(registry, fs), FunkyNameGenerator(names), SliceContainer(fs))
+        return cls(registry, UploadManager(registry, fs), FunkyNameGenerator(names), SliceContainer(fs), uploads_dir)
 
     @classmethod
     def with_failing_loader(cls, uploads_dir="uploads", names=None):
@@ -42,10 +45,10 @@ class RequestContext:
     def production(cls, uploads_dir="uploads", names=None):
         """Process-wide singletons, like the reference (slices.py:94-95, uploads.py:217-218)."""
         global _PROD
-        if _PROD is None or _PROD.registry.root != uploads_dir:
+        if _PROD is None or _PROD.uploads_dir != uploads_dir:
             fs = DiskFS()
             registry = UploadRegistry(uploads_dir)
-            _PROD = cls(registry, UploadManager(registry, fs), FunkyNameGenerator(names), SliceContainer(fs))
+            _PROD = cls(registry, UploadManager(registry, fs), FunkyNameGenerator(names), SliceContainer(fs), uploads_dir)
         return _PROD
 
 

@@ -44,12 +44,24 @@ struct GgjtFile {
         }
     }
 
+    // A throwing constructor never runs the destructor: parse() may throw on a malformed file, so the fd and the
+    // mapping are released here before the exception leaves (a long-running node must not leak them per bad upload).
     explicit GgjtFile(const std::string & path, bool keep_vocab) {
+        try { parse(path, keep_vocab); }
+        catch (...) { release(); throw; }
+    }
+    void release() {
+        if (base) { munmap((void *) base, size); base = nullptr; }
+        if (fd >= 0) { ::close(fd); fd = -1; }
+    }
+    void parse(const std::string & path, bool keep_vocab) {
         fd = ::open(path.c_str(), O_RDONLY);
         if (fd < 0) throw std::runtime_error("cannot open " + path);
-        struct stat st; fstat(fd, &st); size = (size_t) st.st_size;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || st.st_size <= 0) throw std::runtime_error("cannot stat (or empty file) " + path);
+        size = (size_t) st.st_size;
         void * p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (p == MAP_FAILED) { ::close(fd); fd = -1; throw std::runtime_error("mmap failed for " + path); }
+        if (p == MAP_FAILED) throw std::runtime_error("mmap failed for " + path);
         base = (const uint8_t *) p;
         size_t pos = 0;
         auto u32 = [&]() -> uint32_t {
@@ -89,10 +101,7 @@ struct GgjtFile {
             tensors.push_back(std::move(t));
         }
     }
-    ~GgjtFile() {
-        if (base) munmap((void *) base, size);
-        if (fd >= 0) ::close(fd);
-    }
+    ~GgjtFile() { release(); }
     GgjtFile(const GgjtFile &) = delete;
     GgjtFile & operator=(const GgjtFile &) = delete;
 

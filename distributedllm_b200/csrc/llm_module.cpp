@@ -12,21 +12,36 @@
 // RuntimeError instead of printing and leaving a half-built slice (tensor_processor.cpp:1506-1509); a non-float
 // list element raises TypeError instead of returning NULL with no exception set (2115-2117, 2137-2139);
 // `propagate_forward_buffer(bytes-like f32) -> bytes` avoids the per-float list marshalling; the extra-layers
-// file is parsed once per path, not on every call.  Device / context come from B200_DEVICE / B200_N_CTX.
+// file is parsed once per path, not on every call.  Context length, GPU ordinal and session count are LOAD METADATA:
+// load_slice(path, n_ctx=0, device=-1, n_sessions=0) -- keyword extras the reference hard-codes
+// (tensor_processor.cpp:1997-2006); unset values fall back to B200_N_CTX / B200_DEVICE / B200_SESSIONS, then 512 / 0 / 1.
+// The loaded slice is reference-counted: a forward holds its reference for the whole GPU call, load/unload swap the
+// pointer and the last user frees it, so an unload racing an in-flight propagate_forward (ThreadingTCPServer) is safe.
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 
+#include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b200_slice.h"
 
-static b200_slice_t * g_slice = nullptr;                 // one slice per process, like the reference (line 1992)
+struct SliceRef {                                         // frees the slice when the last user drops it
+    b200_slice_t * h;
+    explicit SliceRef(b200_slice_t * p) : h(p) {}
+    ~SliceRef() { if (h) b200_slice_unload(h); }
+};
+typedef std::shared_ptr<SliceRef> SlicePtr;
+static SlicePtr g_slice;                                  // one slice per process, like the reference (line 1992)
 static std::map<std::string, b200_extra_t *> g_extra;
 static std::mutex g_mu;
+static SlicePtr current_slice() { std::lock_guard<std::mutex> lk(g_mu); return g_slice; }
 
 static int env_int(const char * n, int d) { const char * v = getenv(n); return v ? atoi(v) : d; }
 
@@ -35,9 +50,20 @@ static PyObject * raise_b200(const char * what) {
     return nullptr;
 }
 
+// list[float] (the reference's argument type) or any C-contiguous buffer of 4-byte floats (bytes / bytearray are taken
+// as raw float32; typed buffers must say 'f')
 static bool list_to_floats(PyObject * obj, std::vector<float> & out) {
     Py_buffer view;
-    if (!PyList_Check(obj) && PyObject_CheckBuffer(obj) && PyObject_GetBuffer(obj, &view, PyBUF_CONTIG_RO) == 0) {
+    if (!PyList_Check(obj) && PyObject_CheckBuffer(obj)) {
+        if (PyObject_GetBuffer(obj, &view, PyBUF_C_CONTIGUOUS | PyBUF_FORMAT) != 0) return false;
+        const char * f = view.format;
+        const bool raw = !f || !strcmp(f, "B") || !strcmp(f, "b") || !strcmp(f, "c");
+        const bool f32 = f && (!strcmp(f, "f") || !strcmp(f, "<f") || !strcmp(f, "=f") || !strcmp(f, "@f")) && view.itemsize == 4;
+        if ((!raw && !f32) || view.len % 4) {
+            PyBuffer_Release(&view);
+            PyErr_SetString(PyExc_TypeError, "tensor buffer must hold float32 values (format 'f', or raw bytes of length 4*n)");
+            return false;
+        }
         out.assign((const float *) view.buf, (const float *) view.buf + view.len / sizeof(float));
         PyBuffer_Release(&view);
         return true;
@@ -72,52 +98,87 @@ static b200_extra_t * extra_for(const char * path) {
     return e;
 }
 
+// Detach the loaded slice and free it once every in-flight call has dropped its reference (GIL released by the caller).
+static void retire_slice() {
+    SlicePtr old;
+    { std::lock_guard<std::mutex> lk(g_mu); old.swap(g_slice); }
+    while (old && old.use_count() > 1) std::this_thread::sleep_for(std::chrono::microseconds(200));
+    old.reset();                                          // last reference: b200_slice_unload runs here
+}
+
 // ---- node side ---------------------------------------------------------------------------------------------
-static PyObject * py_load_slice(PyObject *, PyObject * args) {
+static PyObject * py_load_slice(PyObject *, PyObject * args, PyObject * kwargs) {
     const char * path;
-    if (!PyArg_ParseTuple(args, "s", &path)) return nullptr;
+    int n_ctx = 0, device = -1, n_sessions = 0;
+    static const char * kw[] = {"path", "n_ctx", "device", "n_sessions", nullptr};
+    if (!PyArg_ParseTupleAndKeywords(args, kwargs, "s|iii", (char **) kw, &path, &n_ctx, &device, &n_sessions)) return nullptr;
+    if (n_ctx <= 0) n_ctx = env_int("B200_N_CTX", 0);
+    if (device < 0) device = env_int("B200_DEVICE", 0);
+    if (n_sessions <= 0) n_sessions = env_int("B200_SESSIONS", 1);
     b200_slice_t * s = nullptr;
     int rc;
     Py_BEGIN_ALLOW_THREADS
-    rc = b200_slice_load_ex(path, env_int("B200_DEVICE", 0), env_int("B200_N_CTX", 0), env_int("B200_SESSIONS", 1), &s);
+    // the old slice goes first (the reference leaks it, line 2006): peak HBM is one slice, not two
+    retire_slice();
+    rc = b200_slice_load_ex(path, device, n_ctx, n_sessions, &s);
     Py_END_ALLOW_THREADS
     if (rc) return raise_b200("load_slice");
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_slice) b200_slice_unload(g_slice);              // the reference leaks the old slice (line 2006); we free it
-    g_slice = s;
+    SlicePtr fresh = std::make_shared<SliceRef>(s), old;
+    { std::lock_guard<std::mutex> lk(g_mu); old.swap(g_slice); g_slice = fresh; }
+    Py_BEGIN_ALLOW_THREADS
+    old.reset();                                          // a concurrent load_slice slipped one in: free it too
+    Py_END_ALLOW_THREADS
     return PyLong_FromLong(0);
 }
 
 static PyObject * py_unload_slice(PyObject *, PyObject *) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_slice) { b200_slice_unload(g_slice); g_slice = nullptr; }
+    Py_BEGIN_ALLOW_THREADS
+    retire_slice();
+    Py_END_ALLOW_THREADS
     return PyLong_FromLong(0);
 }
 
 static PyObject * py_clear_context(PyObject *, PyObject *) {
-    if (g_slice && b200_slice_clear(g_slice) != 0) return PyLong_FromLong(1);
-    return PyLong_FromLong(0);
+    SlicePtr sp = current_slice();
+    int rc = 0;
+    Py_BEGIN_ALLOW_THREADS
+    if (sp) rc = b200_slice_clear(sp->h);
+    sp.reset();
+    Py_END_ALLOW_THREADS
+    return PyLong_FromLong(rc != 0 ? 1 : 0);
 }
 
-static int forward_vec(std::vector<float> & x, std::vector<float> & y) {
+// slice_info() -> dict (additive): what the node reports about the slice it serves
+static PyObject * py_slice_info(PyObject *, PyObject *) {
+    SlicePtr sp = current_slice();
+    if (!sp) Py_RETURN_NONE;
+    b200_slice_info_t i;
+    if (b200_slice_info(sp->h, &i)) return raise_b200("slice_info");
+    return Py_BuildValue("{s:i,s:i,s:i,s:i,s:i,s:i,s:i,s:i,s:i,s:L}", "n_embd", i.n_embd, "n_head", i.n_head, "n_ff", i.n_ff,
+                         "n_layer", i.n_layer, "first_layer", i.first_layer, "n_ctx", i.n_ctx, "n_past", i.n_past,
+                         "device", i.device, "n_sessions", b200_session_count(sp->h), "weight_bytes", (long long) i.weight_bytes);
+}
+
+static int forward_vec(const SlicePtr & sp, std::vector<float> & x, std::vector<float> & y) {
     b200_slice_info_t info;
-    if (!g_slice || b200_slice_info(g_slice, &info)) return -1;
+    if (!sp || b200_slice_info(sp->h, &info)) return -1;
     const int n_tokens = (int)(x.size() / (size_t) info.n_embd);       // N = len / n_embd (tensor_processor.cpp:1526)
     y.resize((size_t) n_tokens * info.n_embd);
-    int rc;
-    Py_BEGIN_ALLOW_THREADS
-    rc = b200_slice_forward(g_slice, x.data(), n_tokens, y.data());
-    Py_END_ALLOW_THREADS
-    return rc;
+    return b200_slice_forward(sp->h, x.data(), n_tokens, y.data());
 }
 
 static PyObject * py_propagate_forward(PyObject *, PyObject * args) {
     PyObject * values;
     if (!PyArg_ParseTuple(args, "O", &values)) return nullptr;
-    if (!g_slice) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward: no slice loaded"); return nullptr; }
+    SlicePtr sp = current_slice();
+    if (!sp) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward: no slice loaded"); return nullptr; }
     std::vector<float> x, y;
     if (!list_to_floats(values, x)) return nullptr;
-    const int rc = forward_vec(x, y);
+    int rc;
+    Py_BEGIN_ALLOW_THREADS
+    rc = forward_vec(sp, x, y);
+    sp.reset();
+    Py_END_ALLOW_THREADS
     if (rc != 0) return PyLong_FromLong(rc);                            // like the reference: an int status (line 2148-2151)
     return floats_to_list(y.data(), y.size());
 }
@@ -125,40 +186,50 @@ static PyObject * py_propagate_forward(PyObject *, PyObject * args) {
 static PyObject * py_propagate_forward_buffer(PyObject *, PyObject * args) {
     PyObject * values;
     if (!PyArg_ParseTuple(args, "O", &values)) return nullptr;
-    if (!g_slice) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward: no slice loaded"); return nullptr; }
+    SlicePtr sp = current_slice();
+    if (!sp) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward: no slice loaded"); return nullptr; }
     std::vector<float> x, y;
     if (!list_to_floats(values, x)) return nullptr;
-    const int rc = forward_vec(x, y);
-    if (rc != 0) return raise_b200("propagate_forward");
+    int rc; std::string err;
+    Py_BEGIN_ALLOW_THREADS
+    rc = forward_vec(sp, x, y);
+    if (rc) err = b200_last_error();
+    sp.reset();
+    Py_END_ALLOW_THREADS
+    if (rc != 0) { PyErr_Format(PyExc_RuntimeError, "propagate_forward: %s", err.c_str()); return nullptr; }
     return PyBytes_FromStringAndSize((const char *) y.data(), (Py_ssize_t)(y.size() * sizeof(float)));
 }
 
-// ---- additive: several sequences on one node (B200_SESSIONS contexts over the same weights) ------------------
+// ---- additive: several sequences on one node (n_sessions contexts over the same weights) ------------------
 // propagate_forward_session(session, float32 bytes-like) -> bytes        tokens of ONE session
 // propagate_forward_batch([sessions], float32 bytes-like) -> bytes       one token for EACH listed session, one pass
 // clear_session(session)  (-1 = all)
 static PyObject * py_propagate_forward_session(PyObject *, PyObject * args) {
     int session; PyObject * values;
     if (!PyArg_ParseTuple(args, "iO", &session, &values)) return nullptr;
-    if (!g_slice) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward_session: no slice loaded"); return nullptr; }
+    SlicePtr sp = current_slice();
+    if (!sp) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward_session: no slice loaded"); return nullptr; }
     std::vector<float> x, y;
     if (!list_to_floats(values, x)) return nullptr;
     b200_slice_info_t info;
-    if (b200_slice_info(g_slice, &info)) return raise_b200("propagate_forward_session");
+    if (b200_slice_info(sp->h, &info)) return raise_b200("propagate_forward_session");
     const int n_tokens = (int)(x.size() / (size_t) info.n_embd);
     y.resize((size_t) n_tokens * info.n_embd);
-    int rc;
+    int rc; std::string err;
     Py_BEGIN_ALLOW_THREADS
-    rc = b200_session_forward(g_slice, session, x.data(), n_tokens, y.data());
+    rc = b200_session_forward(sp->h, session, x.data(), n_tokens, y.data());
+    if (rc) err = b200_last_error();
+    sp.reset();
     Py_END_ALLOW_THREADS
-    if (rc) return raise_b200("propagate_forward_session");
+    if (rc) { PyErr_Format(PyExc_RuntimeError, "propagate_forward_session: %s", err.c_str()); return nullptr; }
     return PyBytes_FromStringAndSize((const char *) y.data(), (Py_ssize_t)(y.size() * sizeof(float)));
 }
 
 static PyObject * py_propagate_forward_batch(PyObject *, PyObject * args) {
     PyObject * sessions, * values;
     if (!PyArg_ParseTuple(args, "OO", &sessions, &values)) return nullptr;
-    if (!g_slice) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward_batch: no slice loaded"); return nullptr; }
+    SlicePtr sp = current_slice();
+    if (!sp) { PyErr_SetString(PyExc_RuntimeError, "propagate_forward_batch: no slice loaded"); return nullptr; }
     if (!PyList_Check(sessions)) { PyErr_SetString(PyExc_TypeError, "propagate_forward_batch: sessions must be a list of int"); return nullptr; }
     std::vector<int> ids((size_t) PyList_Size(sessions));
     for (size_t i = 0; i < ids.size(); i++) {
@@ -169,24 +240,27 @@ static PyObject * py_propagate_forward_batch(PyObject *, PyObject * args) {
     std::vector<float> x, y;
     if (!list_to_floats(values, x)) return nullptr;
     b200_slice_info_t info;
-    if (b200_slice_info(g_slice, &info)) return raise_b200("propagate_forward_batch");
+    if (b200_slice_info(sp->h, &info)) return raise_b200("propagate_forward_batch");
     if (x.size() != ids.size() * (size_t) info.n_embd) {
         PyErr_SetString(PyExc_ValueError, "propagate_forward_batch: need exactly one n_embd row per listed session");
         return nullptr;
     }
     y.resize(x.size());
-    int rc;
+    int rc; std::string err;
     Py_BEGIN_ALLOW_THREADS
-    rc = b200_batch_forward(g_slice, ids.data(), (int) ids.size(), x.data(), y.data());
+    rc = b200_batch_forward(sp->h, ids.data(), (int) ids.size(), x.data(), y.data());
+    if (rc) err = b200_last_error();
+    sp.reset();
     Py_END_ALLOW_THREADS
-    if (rc) return raise_b200("propagate_forward_batch");
+    if (rc) { PyErr_Format(PyExc_RuntimeError, "propagate_forward_batch: %s", err.c_str()); return nullptr; }
     return PyBytes_FromStringAndSize((const char *) y.data(), (Py_ssize_t)(y.size() * sizeof(float)));
 }
 
 static PyObject * py_clear_session(PyObject *, PyObject * args) {
     int session;
     if (!PyArg_ParseTuple(args, "i", &session)) return nullptr;
-    if (g_slice && b200_session_clear(g_slice, session) != 0) return raise_b200("clear_session");
+    SlicePtr sp = current_slice();
+    if (sp && b200_session_clear(sp->h, session) != 0) return raise_b200("clear_session");
     return PyLong_FromLong(0);
 }
 
@@ -280,7 +354,8 @@ static PyObject * py_decode_token(PyObject *, PyObject * args) {
 }
 
 static PyMethodDef Methods[] = {
-    {"load_slice", py_load_slice, METH_VARARGS, "Load all transformer block layers in the slice onto the GPU"},
+    {"load_slice", (PyCFunction)(void (*)(void)) py_load_slice, METH_VARARGS | METH_KEYWORDS, "load_slice(path, n_ctx=0, device=-1, n_sessions=0): load the slice's layers onto the GPU"},
+    {"slice_info", py_slice_info, METH_NOARGS, "dict describing the loaded slice (None if none)"},
     {"unload_slice", py_unload_slice, METH_VARARGS, "Unload the slice currently loaded"},
     {"clear_context", py_clear_context, METH_VARARGS, "Clear cached keys and values"},
     {"tokenize_prompt", py_tokenize_prompt, METH_VARARGS, "Convert a text prompt into a list of tokens"},

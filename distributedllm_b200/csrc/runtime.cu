@@ -8,12 +8,17 @@
 #include "fastgemm.cuh"
 #include "ggjt_file.hpp"
 
+#include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <dlfcn.h>
 #include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace b200 {
@@ -60,7 +65,8 @@ struct b200_slice {
     bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true;
     bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
-    int opt_ns = 0, opt_cta_per_sm = 0, opt_nc = 0;
+    int opt_ns = 0, opt_cta_per_sm = 0, opt_nc = 0, opt_pre = 3, opt_nomath = 0;   // read once at load (environment)
+    float ema_token_ms = 0.f;              // host-buffer decode calls: smoothed device time of one token (sleep-then-poll wait)
     std::mutex mu;
     // per-kernel-class event timing (b200_slice_profile): class 0 qkv, 1 rope, 2 attention, 3 wo, 4 w13, 5 w2, 6 advance
     bool profiling = false; int cur_class = 0;
@@ -130,7 +136,7 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[s->device & 15] = true;
     }
-    a.NS = NS; a.dbg_nomath = env_int("B200_DBG_NOMATH", 0); a.pre_stages = env_int("B200_PRE", 3);
+    a.NS = NS; a.dbg_nomath = s->opt_nomath; a.pre_stages = s->opt_pre;
     a.trace = nullptr;
     if (s->trace && s->trace_next < 512) { a.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(s->cur_class); }
     int per_sm = s->opt_cta_per_sm > 0 ? s->opt_cta_per_sm : (int)(kSmemLimit / (smem + 1024));
@@ -448,10 +454,15 @@ static int forward_locked(b200_slice * s, const float * in, int N, float * out, 
             memcpy(s->h_in, in, (size_t) s->E * 4);
             if ((rc = run_decode_graph(s, nullptr, nullptr, true))) return rc;
             B200_CUDA(cudaEventRecord(s->ev1, s->stream));
-            // a decoded token is ~1 ms of GPU work: poll for its completion (a blocking synchronize adds the wake-up
-            // latency of the driver's interrupt path to every token), fall back to blocking if it takes unusually long
-            for (int spin = 0; spin < 200000; spin++) if (cudaEventQuery(s->ev1) != cudaErrorNotReady) break;
+            // A decoded token is ~1 ms of GPU work.  A blocking synchronize adds the wake-up latency of the driver's
+            // interrupt path to every token; polling from the start burns a core for the whole token.  So: sleep through
+            // ~70 % of the smoothed token time, poll the rest, and block if the token takes unusually long.
+            if (s->ema_token_ms > 0.2f)
+                std::this_thread::sleep_for(std::chrono::microseconds((long)(700.f * s->ema_token_ms)));
+            for (int spin = 0; spin < 100000; spin++) if (cudaEventQuery(s->ev1) != cudaErrorNotReady) break;
             B200_CUDA(cudaStreamSynchronize(s->stream));
+            { float ms = 0.f; if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess && ms > 0.f)
+                  s->ema_token_ms = s->ema_token_ms > 0.f ? 0.8f * s->ema_token_ms + 0.2f * ms : ms; }
             memcpy(out, s->h_out, (size_t) s->E * 4);
         } else {
             B200_CUDA(cudaMemcpyAsync(s->d_in, in, (size_t) N * s->E * 4, cudaMemcpyHostToDevice, s->stream));
@@ -511,55 +522,120 @@ static int batch_locked(b200_slice * s, const int * sessions, int B, const float
 }
 
 // ---------------------------------------------------------------- loader
-// Pageable H2D copies return before the DMA lands; keep them on the slice's stream so the
-// repack kernel that follows is ordered after them.
-static int upload_raw(b200_slice * s, const GgjtFile & f, const GgjtTensor & t, uint8_t * dst) {
-    B200_CUDA(cudaMemcpyAsync(dst, f.data(t), t.nbytes, cudaMemcpyHostToDevice, s->stream));
-    return 0;
-}
+// file (mmap, page cache) --reader thread--> pinned staging ring --DMA--> device scratch ring --k_repack--> packed HBM.
+// Three slots are in flight: while slot j is repacked on the GPU, slot j+1 is on the PCIe bus and the reader thread is
+// faulting slot j+2 in from the page cache.  Nothing synchronises the stream per matrix; a slot is reused once the
+// event recorded behind its repack kernel has completed (the reader thread waits for it).
+struct LoadJob {
+    const GgjtTensor * src[3] = {nullptr, nullptr, nullptr};
+    int nsrc = 0;
+    int kind = 0;                 // 0: block-quantised matrix (k_repack), 1: F16 (k_repack_f16), 2: raw copy, 3: Q6_K (k_repack_q6k)
+    int mode = 0, G = 1;
+    PackedW * out = nullptr;      // kind 0
+    uint16_t ** outf = nullptr; uint16_t * into = nullptr;   // kind 1
+    uint8_t * raw_dst = nullptr;  // kind 2
+    size_t bytes() const { size_t n = 0; for (int i = 0; i < nsrc; i++) n += (src[i]->nbytes + 255) & ~(size_t) 255; return n; }
+};
 
-static int pack_matrix(b200_slice * s, const GgjtFile & f, const GgjtTensor * const * src, int nsrc, int mode, int G,
-                       uint8_t * scratch, PackedW * out) {
-    const int wt = (int) src[0]->type;
-    const int K = (int) src[0]->ne[0], rows_per = (int) src[0]->ne[1];
-    const int nb = K / 32, nbq = ((nb + 3) / 4 + kQS - 1) / kQS * kQS, TR = kWPC * G;
-    const int total_groups = (rows_per + 7) / 8 * nsrc;
-    const int n_tiles = (total_groups + TR - 1) / TR;
-    const int cb = chunk_bytes(wt);
-    const long long tile_bytes = (long long) nbq * TR * cb;
-    uint8_t * dst = nullptr;
-    int rc = dev_alloc(s, &dst, (size_t) n_tiles * tile_bytes);
-    if (rc) return rc;
-    RepackArgs ra{};
-    size_t off = 0;
-    for (int i = 0; i < nsrc; i++) {
-        if ((rc = upload_raw(s, f, *src[i], scratch + off))) return rc;
-        ra.src[i] = scratch + off;
-        off += (src[i]->nbytes + 255) & ~(size_t) 255;
+struct LoadPipe {
+    static constexpr int NB = 3;
+    uint8_t * pinned[NB] = {nullptr, nullptr, nullptr};
+    uint8_t * scratch[NB] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr};
+    size_t slot_bytes = 0;
+    ~LoadPipe() {
+        for (int i = 0; i < NB; i++) {
+            if (pinned[i]) cudaFreeHost(pinned[i]);
+            if (scratch[i]) cudaFree(scratch[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
     }
-    ra.mode = mode; ra.wtype = wt; ra.rows_per_src = rows_per; ra.nb = nb; ra.nbq = nbq; ra.TR = TR; ra.n_tiles = n_tiles;
-    ra.dst = dst;
-    k_repack<<<s->n_sm * 8, 256, 0, s->stream>>>(ra);
-    B200_CUDA(cudaGetLastError());
-    B200_CUDA(cudaStreamSynchronize(s->stream));
-    out->data = dst; out->wtype = wt; out->rows = rows_per * nsrc; out->K = K; out->nb = nb; out->nbq = nbq; out->TR = TR;
-    out->n_tiles = n_tiles; out->tile_bytes = tile_bytes;
-    return 0;
-}
+};
 
-// `into`: pack into an existing buffer (wq | wk | wv share one, so the three matmuls are one launch over 3E rows)
-static int pack_f16(b200_slice * s, const GgjtFile & f, const GgjtTensor & t, uint8_t * scratch, uint16_t ** out, uint16_t * into = nullptr) {
-    const int K = (int) t.ne[0], rows = (int) t.ne[1];
-    const int nchunk = K / 32, nc8 = (nchunk + 7) / 8;
-    uint16_t * dst = into;
-    int rc;
-    if (!dst && (rc = dev_alloc(s, &dst, (size_t) rows * nc8 * 256 + 8))) return rc;
-    if ((rc = upload_raw(s, f, t, scratch))) return rc;
-    k_repack_f16<<<s->n_sm * 8, 256, 0, s->stream>>>((const uint16_t *) scratch, dst, dst /*no tail: K%32==0*/, rows, K);
-    B200_CUDA(cudaGetLastError());
-    B200_CUDA(cudaStreamSynchronize(s->stream));
-    *out = dst;
-    return 0;
+static int run_load_jobs(b200_slice * s, const GgjtFile & f, std::vector<LoadJob> & jobs) {
+    if (jobs.empty()) return 0;
+    LoadPipe lp;
+    for (const LoadJob & j : jobs) lp.slot_bytes = std::max(lp.slot_bytes, j.bytes());
+    lp.slot_bytes += 4096;
+    for (int i = 0; i < LoadPipe::NB; i++) {
+        B200_CUDA(cudaMallocHost((void **) &lp.pinned[i], lp.slot_bytes));
+        B200_CUDA(cudaMalloc((void **) &lp.scratch[i], lp.slot_bytes));
+        B200_CUDA(cudaEventCreateWithFlags(&lp.ev[i], cudaEventDisableTiming));
+    }
+    madvise((void *) f.base, f.size, MADV_WILLNEED);       // start the kernel's read-ahead for a cold file
+    std::mutex mu; std::condition_variable cv;
+    size_t filled = 0, consumed = 0; bool abort_flag = false;
+    const int device = s->device;
+    std::thread reader([&] {
+        cudaSetDevice(device);
+        for (size_t j = 0; j < jobs.size(); j++) {
+            const int slot = (int)(j % LoadPipe::NB);
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return abort_flag || consumed + LoadPipe::NB > j; });
+                if (abort_flag) return;
+            }
+            if (j >= LoadPipe::NB) cudaEventSynchronize(lp.ev[slot]);    // the slot's previous repack has read its scratch
+            size_t off = 0;
+            for (int i = 0; i < jobs[j].nsrc; i++) {
+                memcpy(lp.pinned[slot] + off, f.data(*jobs[j].src[i]), jobs[j].src[i]->nbytes);
+                off += (jobs[j].src[i]->nbytes + 255) & ~(size_t) 255;
+            }
+            { std::lock_guard<std::mutex> lk(mu); filled = j + 1; }
+            cv.notify_all();
+        }
+    });
+    int rc = 0;
+    for (size_t j = 0; j < jobs.size() && !rc; j++) {
+        const int slot = (int)(j % LoadPipe::NB);
+        LoadJob & job = jobs[j];
+        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return filled > j; }); }
+        cudaError_t e = cudaMemcpyAsync(lp.scratch[slot], lp.pinned[slot], job.bytes(), cudaMemcpyHostToDevice, s->stream);
+        if (e != cudaSuccess) { rc = fail(B200_ECUDA, "weight upload failed: %s", cudaGetErrorString(e)); break; }
+        if (job.kind == 0) {
+            const int wt = (int) job.src[0]->type;
+            const int K = (int) job.src[0]->ne[0], rows_per = (int) job.src[0]->ne[1];
+            const int nb = K / 32, nbq = ((nb + 3) / 4 + kQS - 1) / kQS * kQS, TR = kWPC * job.G;
+            const int total_groups = (rows_per + 7) / 8 * job.nsrc;
+            const int n_tiles = (total_groups + TR - 1) / TR;
+            const long long tile_bytes = (long long) nbq * TR * chunk_bytes(wt);
+            uint8_t * dst = nullptr;
+            if ((rc = dev_alloc(s, &dst, (size_t) n_tiles * tile_bytes))) break;
+            RepackArgs ra{};
+            size_t off = 0;
+            for (int i = 0; i < job.nsrc; i++) { ra.src[i] = lp.scratch[slot] + off; off += (job.src[i]->nbytes + 255) & ~(size_t) 255; }
+            ra.mode = job.mode; ra.wtype = wt; ra.rows_per_src = rows_per; ra.nb = nb; ra.nbq = nbq; ra.TR = TR; ra.n_tiles = n_tiles;
+            ra.dst = dst;
+            k_repack<<<s->n_sm * 8, 256, 0, s->stream>>>(ra);
+            PackedW * out = job.out;
+            out->data = dst; out->wtype = wt; out->rows = rows_per * job.nsrc; out->K = K; out->nb = nb; out->nbq = nbq; out->TR = TR;
+            out->n_tiles = n_tiles; out->tile_bytes = tile_bytes;
+        } else if (job.kind == 1) {
+            const GgjtTensor & t = *job.src[0];
+            const int K = (int) t.ne[0], rows = (int) t.ne[1];
+            const int nchunk = K / 32, nc8 = (nchunk + 7) / 8;
+            uint16_t * dst = job.into;
+            if (!dst && (rc = dev_alloc(s, &dst, (size_t) rows * nc8 * 256 + 8))) break;
+            k_repack_f16<<<s->n_sm * 8, 256, 0, s->stream>>>((const uint16_t *) lp.scratch[slot], dst, dst /*no tail: K%32==0*/, rows, K);
+            *job.outf = dst;
+        } else if (job.kind == 3) {
+            const GgjtTensor & t = *job.src[0];
+            k_repack_q6k<<<s->n_sm * 8, 256, 0, s->stream>>>(lp.scratch[slot], job.raw_dst, (int) t.ne[1], (int) t.ne[0] / 256);
+        } else {
+            e = cudaMemcpyAsync(job.raw_dst, lp.scratch[slot], job.src[0]->nbytes, cudaMemcpyDeviceToDevice, s->stream);
+            if (e != cudaSuccess) { rc = fail(B200_ECUDA, "weight copy failed: %s", cudaGetErrorString(e)); break; }
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) { rc = fail(B200_ECUDA, "repack launch failed: %s", cudaGetErrorString(e)); break; }
+        cudaEventRecord(lp.ev[slot], s->stream);
+        { std::lock_guard<std::mutex> lk(mu); consumed = j + 1; }
+        cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(mu); abort_flag = rc != 0; consumed = jobs.size() + LoadPipe::NB; }
+    cv.notify_all();
+    reader.join();
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (!rc && e != cudaSuccess) rc = fail(B200_ECUDA, "weight repack failed: %s", cudaGetErrorString(e));
+    return rc;
 }
 
 static int build_tables(b200_slice * s) {
@@ -600,17 +676,32 @@ static int load_locked(b200_slice * s, const char * path) {
     s->E = (int) f.n_embd; s->H = (int) f.n_head; s->D = s->E / s->H; s->L = (int) f.n_layer; s->first_layer = (int) f.first_layer;
     s->FF = (int)(((2 * (4 * f.n_embd) / 3 + f.n_mult - 1) / f.n_mult) * f.n_mult);   // tensor_processor.cpp:1250
     if (s->D > 128 || (s->D & 1)) return fail(B200_EFILE, "head size %d unsupported (<=128, even)", s->D);
+    {
+        // worst-case dynamic shared memory of the attention kernels at this n_ctx (scores f32 + probabilities f16 per
+        // position, + staged rows / exp table / partials): reject the load instead of failing every forward later
+        const size_t sc_bytes = (((size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2) + 15) & ~(size_t) 15;
+        int pf_rows = 8 * ((s->n_ctx + 31) / 32); if (pf_rows > 128) pf_rows = 128;
+        const size_t need128 = sc_bytes + (size_t) 2 * pf_rows * kAttnRow + 32 * 64 + 64 + 65536;
+        const size_t need_gen = (size_t)((s->n_ctx + 3) & ~3) * 4 + (size_t)((s->n_ctx + 7) & ~7) * 2 + (size_t) 4 * s->D * 8 * 4 + 64;
+        const size_t need = s->D == 128 ? need128 : need_gen, limit = s->D == 128 ? (size_t) 200 * 1024 : (size_t) kSmemLimit;
+        if (need > limit)
+            return fail(B200_EINVAL, "n_ctx %d needs %zu B of attention shared memory (limit %zu B): largest supported n_ctx for head size %d is %d",
+                        s->n_ctx, need, limit, s->D, s->D == 128 ? (int)((limit - 2 * 128 * kAttnRow - 32 * 64 - 64 - 65536 - 16) / 6) & ~31
+                                                                 : (int)((limit - (size_t) 4 * s->D * 32 - 64) / 6) & ~31);
+    }
     const uint32_t E = f.n_embd, FF = (uint32_t) s->FF;
     s->layers.resize(s->L);
-    uint8_t * scratch = nullptr;
     int rc;
+    std::vector<LoadJob> jobs;
+    std::vector<float> norms;                       // all norm weights, one upload
     try {
         const std::string p0 = "layers." + std::to_string(s->first_layer);
         s->wtype = (int) f.get(p0 + ".attention.wq.weight", {E, E}).type;
         if (s->wtype != kWT_Q4_0 && s->wtype != kWT_Q8_0 && s->wtype != kWT_F16)
             return fail(B200_EFILE, "weight type %d unsupported (Q4_0, Q8_0, F16)", s->wtype);
-        const size_t big = GgjtFile::type_bytes(s->wtype, (size_t) E * FF) + 4096;
-        B200_CUDA(cudaMalloc((void **) &scratch, 3 * big));
+        float * d_norms = nullptr;
+        if ((rc = dev_alloc(s, &d_norms, (size_t) s->L * 2 * E))) return rc;
+        norms.resize((size_t) s->L * 2 * E);
         for (int i = 0; i < s->L; i++) {
             const std::string p = "layers." + std::to_string(i + s->first_layer);
             LayerW & Lw = s->layers[i];
@@ -623,37 +714,35 @@ static int load_locked(b200_slice * s, const char * path) {
             const GgjtTensor & w1 = f.get(p + ".feed_forward.w1.weight", {E, FF});
             const GgjtTensor & w2 = f.get(p + ".feed_forward.w2.weight", {FF, E});
             const GgjtTensor & w3 = f.get(p + ".feed_forward.w3.weight", {E, FF});
-            if (an.type != GT_F32 || fn.type != GT_F32) { cudaFree(scratch); return fail(B200_EFILE, "norm weights must be F32"); }
+            if (an.type != GT_F32 || fn.type != GT_F32) return fail(B200_EFILE, "norm weights must be F32");
             for (const GgjtTensor * t : {&wq, &wk, &wv, &wo, &w1, &w2, &w3})
-                if ((int) t->type != s->wtype) { cudaFree(scratch); return fail(B200_EFILE, "mixed weight types in slice (%s)", t->name.c_str()); }
-            if ((rc = dev_alloc(s, &Lw.attn_norm, E)) || (rc = dev_alloc(s, &Lw.ffn_norm, E))) { cudaFree(scratch); return rc; }
-            cudaMemcpy(Lw.attn_norm, f.data(an), E * 4, cudaMemcpyHostToDevice);
-            cudaMemcpy(Lw.ffn_norm, f.data(fn), E * 4, cudaMemcpyHostToDevice);
+                if ((int) t->type != s->wtype) return fail(B200_EFILE, "mixed weight types in slice (%s)", t->name.c_str());
+            Lw.attn_norm = d_norms + (size_t) i * 2 * E; Lw.ffn_norm = Lw.attn_norm + E;
+            memcpy(norms.data() + (size_t) i * 2 * E, f.data(an), (size_t) E * 4);
+            memcpy(norms.data() + (size_t) i * 2 * E + E, f.data(fn), (size_t) E * 4);
             if (s->wtype == kWT_F16) {
                 const GgjtTensor * ts[7] = {&wq, &wk, &wv, &wo, &w1, &w2, &w3};
                 uint16_t ** dst[7] = {&Lw.f_q, &Lw.f_k, &Lw.f_v, &Lw.f_o, &Lw.f_1, &Lw.f_2, &Lw.f_3};
                 const size_t per = (size_t) E * ((E / 32 + 7) / 8) * 256;          // packed elements of one E x E matrix
                 uint16_t * qkv_buf = nullptr;
-                if ((rc = dev_alloc(s, &qkv_buf, 3 * per + 8))) { cudaFree(scratch); return rc; }
-                for (int k = 0; k < 7; k++)
-                    if ((rc = pack_f16(s, f, *ts[k], scratch, dst[k], k < 3 ? qkv_buf + k * per : nullptr))) { cudaFree(scratch); return rc; }
+                if ((rc = dev_alloc(s, &qkv_buf, 3 * per + 8))) return rc;
+                for (int k = 0; k < 7; k++) {
+                    LoadJob j; j.kind = 1; j.nsrc = 1; j.src[0] = ts[k]; j.outf = dst[k]; j.into = k < 3 ? qkv_buf + k * per : nullptr;
+                    jobs.push_back(j);
+                }
             } else {
-                const GgjtTensor * qkv[3] = {&wq, &wk, &wv};
-                const GgjtTensor * o1[1] = {&wo};
-                const GgjtTensor * g13[2] = {&w1, &w3};
-                const GgjtTensor * d2[1] = {&w2};
-                if ((rc = pack_matrix(s, f, qkv, 3, 1, 1, scratch, &Lw.qkv)) ||
-                    (rc = pack_matrix(s, f, o1, 1, 0, 1, scratch, &Lw.wo)) ||
-                    (rc = pack_matrix(s, f, g13, 2, 2, 2, scratch, &Lw.w13)) ||
-                    (rc = pack_matrix(s, f, d2, 1, 0, 1, scratch, &Lw.w2))) { cudaFree(scratch); return rc; }
+                LoadJob a; a.nsrc = 3; a.src[0] = &wq; a.src[1] = &wk; a.src[2] = &wv; a.mode = 1; a.G = 1; a.out = &Lw.qkv; jobs.push_back(a);
+                LoadJob o; o.nsrc = 1; o.src[0] = &wo; o.mode = 0; o.G = 1; o.out = &Lw.wo; jobs.push_back(o);
+                LoadJob g; g.nsrc = 2; g.src[0] = &w1; g.src[1] = &w3; g.mode = 2; g.G = 2; g.out = &Lw.w13; jobs.push_back(g);
+                LoadJob d; d.nsrc = 1; d.src[0] = &w2; d.mode = 0; d.G = 1; d.out = &Lw.w2; jobs.push_back(d);
             }
             s->weight_bytes += (int64_t)(an.nbytes + fn.nbytes + wq.nbytes + wk.nbytes + wv.nbytes + wo.nbytes + w1.nbytes + w2.nbytes + w3.nbytes);
         }
+        B200_CUDA(cudaMemcpyAsync(d_norms, norms.data(), norms.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        if ((rc = run_load_jobs(s, f, jobs))) return rc;
     } catch (const std::exception & e) {
-        if (scratch) cudaFree(scratch);
         return fail(B200_EFILE, "error loading model: %s", e.what());
     }
-    cudaFree(scratch);
 
     const size_t nE = (size_t) s->n_ctx * E;
     s->sess_stride = (size_t) s->L * nE;
@@ -746,6 +835,7 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->fast_prefill = env_int("B200_FAST_PREFILL", 0) != 0; s->fast_min_tokens = env_int("B200_FAST_MIN_TOKENS", 32);
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
     s->opt_ns = env_int("B200_NS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
+    s->opt_pre = env_int("B200_PRE", 3); s->opt_nomath = env_int("B200_DBG_NOMATH", 0);
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
     int rc = load_locked(s, path);
@@ -756,7 +846,20 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
 
 int b200_slice_unload(b200_slice_t * s) {
     if (!s) return fail(B200_EINVAL, "null handle");
+    { std::lock_guard<std::mutex> lk(s->mu); }       // let a call that is inside the library finish (see the header: no NEW call may race unload)
     destroy(s);
+    return 0;
+}
+
+/* Create the CUDA context of `device` (cudaSetDevice + a no-op runtime call).  The first CUDA call of a process costs
+ * 0.3 s on a 1-GPU box and several seconds on an 8-GPU box; callers that time b200_slice_load can pay it up front. */
+int b200_device_init(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(B200_ENODEV, "no CUDA device visible: the slice forward has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200_ENODEV, "device %d out of range (%d visible)", device, ndev);
+    B200_CUDA(cudaSetDevice(device));
+    B200_CUDA(cudaFree(nullptr));
     return 0;
 }
 
@@ -1075,6 +1178,23 @@ static int pipeline_step_locked(b200_slice * s, const float * d_in, int n_rows, 
     const size_t count = (size_t) n_rows * s->E;
     const int r = s->pp_rank, W = s->pp_world;
     int rc;
+    // validate the step BEFORE anything is posted: a rejected step must not leave the peer's send unmatched
+    if (sessions) {
+        if (n_rows > s->n_sessions) return fail(B200_EINVAL, "batch of %d sequences with %d sessions", n_rows, s->n_sessions);
+        std::vector<char> seen(s->n_sessions, 0);
+        for (int b = 0; b < n_rows; b++) {
+            const int k = sessions[b];
+            if (k < 0 || k >= s->n_sessions) return fail(B200_EINVAL, "session %d outside [0, %d)", k, s->n_sessions);
+            if (seen[k]) return fail(B200_EINVAL, "session %d listed twice in one batched step", k);
+            seen[k] = 1;
+            if (s->past[k] + 1 > s->n_ctx) return fail(B200_ECONTEXT, "context overflow: session %d n_past %d + 1 > n_ctx %d", k, s->past[k], s->n_ctx);
+        }
+    } else {
+        if (session < 0 || session >= s->n_sessions) return fail(B200_EINVAL, "session %d outside [0, %d)", session, s->n_sessions);
+        if (s->past[session] + n_rows > s->n_ctx)
+            return fail(B200_ECONTEXT, "context overflow: n_past %d + n_tokens %d > n_ctx %d", s->past[session], n_rows, s->n_ctx);
+    }
+    if (r == 0 && !d_in) return fail(B200_EINVAL, "rank 0 needs an input buffer");
     const float * in = d_in;
     if (r > 0) {
         if ((rc = n.Recv(s->d_in, count, kNcclFloat32, r - 1, s->nccl_comm, s->stream))) return nccl_fail("ncclRecv", rc);
@@ -1146,7 +1266,7 @@ struct b200_extra {
     uint8_t * emb_raw = nullptr;          // tok_embeddings as stored (row = token)
     float * norm_w = nullptr;
     PackedW out{}; uint16_t * out_f16 = nullptr; uint8_t * out_q6k = nullptr;
-    float * d_x = nullptr, * d_logits = nullptr; int32_t * d_tok = nullptr; int cap_tokens = 0;
+    float * d_x = nullptr, * d_logits = nullptr; int32_t * d_tok = nullptr, * d_best = nullptr; int cap_tokens = 0;
     std::vector<std::pair<std::string, float>> vocab;
     std::unordered_map<std::string, int> token_to_id;
     std::mutex mu;
@@ -1177,11 +1297,43 @@ __global__ void k_embed_rows(const uint8_t * emb, int type, int E, const int32_t
 static int extra_reserve(b200_extra * e, int n) {
     if (n <= e->cap_tokens) return 0;
     b200_slice * s = &e->ctx;
+    // growth: release the old staging buffers first (they are tracked in `allocs` for unload)
+    cudaStreamSynchronize(s->stream);
+    for (void * old : {(void *) e->d_x, (void *) e->d_logits, (void *) e->d_tok, (void *) e->d_best}) {
+        if (!old) continue;
+        s->allocs.erase(std::remove(s->allocs.begin(), s->allocs.end(), old), s->allocs.end());
+        cudaFree(old);
+    }
+    e->d_x = nullptr; e->d_logits = nullptr; e->d_tok = nullptr; e->d_best = nullptr; e->cap_tokens = 0;
     int rc;
     if ((rc = dev_alloc(s, &e->d_x, (size_t) n * e->E)) || (rc = dev_alloc(s, &e->d_logits, (size_t) n * e->n_vocab)) ||
-        (rc = dev_alloc(s, &e->d_tok, (size_t) n))) return rc;
+        (rc = dev_alloc(s, &e->d_tok, (size_t) n)) || (rc = dev_alloc(s, &e->d_best, (size_t) 1))) return rc;
     e->cap_tokens = n;
     return 0;
+}
+
+// sample_next_token (tensor_processor.cpp:1894-1908): best = -1e12, id = 0; `if (logit > best)` in index order, i.e. the
+// FIRST maximum wins, NaNs never win, and a row that never exceeds -1e12 yields id 0.  One block over the row.
+__global__ void __launch_bounds__(1024) k_argmax_first(const float * logits, int n, int32_t * out) {
+    __shared__ float sv[32]; __shared__ int si[32];
+    float bv = -(1000000000000.0f); int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = logits[i]; if (v > bv) { bv = v; bi = i; } }
+    auto better = [](float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); };
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v = __shfl_xor_sync(0xffffffffu, bv, o); const int i = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        bv = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -(1000000000000.0f);
+        bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v = __shfl_xor_sync(0xffffffffu, bv, o); const int i = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(v, i, bv, bi)) { bv = v; bi = i; }
+        }
+        if (threadIdx.x == 0) *out = bi == 0x7fffffff ? 0 : bi;
+    }
 }
 
 // sentencepiece-style greedy bigram merging, as tensor_processor.cpp:1596-1714 specifies it:
@@ -1263,21 +1415,17 @@ int b200_extra_load(const char * path, int device, b200_extra_t ** out) {
         if (to.type == GT_Q6_K && E % 256) return fail(B200_EFILE, "Q6_K output.weight needs n_embd %% 256 == 0");
         if (tn.type != GT_F32) return fail(B200_EFILE, "norm.weight must be F32");
         if ((rc = dev_alloc(s, &e->emb_raw, te.nbytes)) || (rc = dev_alloc(s, &e->norm_w, (size_t) E))) return rc;
-        B200_CUDA(cudaMemcpyAsync(e->emb_raw, f.data(te), te.nbytes, cudaMemcpyHostToDevice, s->stream));
         B200_CUDA(cudaMemcpyAsync(e->norm_w, f.data(tn), (size_t) E * 4, cudaMemcpyHostToDevice, s->stream));
-        uint8_t * scratch = nullptr;
-        B200_CUDA(cudaMalloc((void **) &scratch, to.nbytes + 4096));
+        std::vector<LoadJob> jobs;
+        LoadJob je; je.kind = 2; je.nsrc = 1; je.src[0] = &te; je.raw_dst = e->emb_raw; jobs.push_back(je);
+        LoadJob jo; jo.nsrc = 1; jo.src[0] = &to;
         if (to.type == GT_Q6_K) {
-            const int nb256 = (int) E / 256;
-            if (!(rc = dev_alloc(s, &e->out_q6k, (size_t) V * nb256 * kQ6Packed)) && !(rc = upload_raw(s, f, to, scratch))) {
-                k_repack_q6k<<<s->n_sm * 8, 256, 0, s->stream>>>(scratch, e->out_q6k, (int) V, nb256);
-                if (cudaGetLastError() != cudaSuccess) rc = fail(B200_ECUDA, "k_repack_q6k launch failed");
-            }
-        } else if (to.type == GT_F16) rc = pack_f16(s, f, to, scratch, &e->out_f16);
-        else { const GgjtTensor * src[1] = {&to}; rc = pack_matrix(s, f, src, 1, 0, 1, scratch, &e->out); }
-        B200_CUDA(cudaStreamSynchronize(s->stream));
-        cudaFree(scratch);
-        if (rc) return rc;
+            if ((rc = dev_alloc(s, &e->out_q6k, (size_t) V * (E / 256) * kQ6Packed))) return rc;
+            jo.kind = 3; jo.raw_dst = e->out_q6k;
+        } else if (to.type == GT_F16) { jo.kind = 1; jo.outf = &e->out_f16; }
+        else { jo.kind = 0; jo.mode = 0; jo.G = 1; jo.out = &e->out; }
+        jobs.push_back(jo);
+        if ((rc = run_load_jobs(s, f, jobs))) return rc;
     } catch (const std::exception & ex) { return fail(B200_EFILE, "error loading extra layers: %s", ex.what()); }
     // fp16 SiLU table is not needed here, but the launch helper wants events
     B200_CUDA(cudaEventCreate(&s->ev0));
@@ -1366,12 +1514,19 @@ int b200_extra_logits(b200_extra_t * e, const float * emb, int n_tokens, int all
 
 int b200_extra_next_token(b200_extra_t * e, const float * emb, int n_tokens, int32_t * token) {
     if (!e || !emb || !token || n_tokens <= 0) return fail(B200_EINVAL, "bad argument");
-    std::vector<float> logits((size_t) e->n_vocab);
-    int rc = b200_extra_logits(e, emb, n_tokens, 0, logits.data());
+    std::lock_guard<std::mutex> lk(e->mu);
+    b200_slice * s = &e->ctx;
+    B200_CUDA(cudaSetDevice(s->device));
+    // only the LAST token's logits decide (get_llm_output + sample_next_token, tensor_processor.cpp:1787-1908); rows of
+    // the lm_head are independent, so computing that row alone is the same arithmetic.  The argmax runs on the device:
+    // 4 bytes come back instead of n_vocab floats.
+    int rc = extra_logits_device(e, emb + (size_t)(n_tokens - 1) * e->E, 1);
     if (rc) return rc;
-    float best = -(1000000000000.0f); int32_t id = 0;          // sample_next_token, tensor_processor.cpp:1894-1908
-    for (size_t i = 0; i < logits.size(); i++) if (logits[i] > best) { best = logits[i]; id = (int32_t) i; }
-    *token = id;
+    k_argmax_first<<<1, 1024, 0, s->stream>>>(e->d_logits, e->n_vocab, e->d_best);
+    B200_CUDA(cudaGetLastError());
+    s->launches++;
+    B200_CUDA(cudaMemcpyAsync(token, e->d_best, 4, cudaMemcpyDeviceToHost, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
 

@@ -50,8 +50,14 @@ typedef struct b200_slice_info {
  * n_ctx <= 0 selects the reference default, 512 (vendor examples/common.h:28). */
 int b200_slice_load(const char * path, int device, int n_ctx, b200_slice_t ** out);
 
-/* llm.unload_slice()  (tensor_processor.cpp:2023-2030). */
+/* llm.unload_slice()  (tensor_processor.cpp:2023-2030).  Waits for a call that is already inside the library on this
+ * handle; the caller must not START another call on the handle concurrently with (or after) unload -- the `llm` module
+ * guarantees that with a reference count (csrc/llm_module.cpp). */
 int b200_slice_unload(b200_slice_t * s);
+
+/* Create the CUDA context of `device` ahead of the first load (the first CUDA call of a process takes 0.3 s on a 1-GPU
+ * box, seconds on an 8-GPU box); optional, lets a caller time b200_slice_load without it. */
+int b200_device_init(int device);
 
 /* llm.clear_context()  (tensor_processor.cpp:2012-2021, TransformerSlice::clear_context 1512-1521):
  * n_past = 0; the cache contents become unreachable. */

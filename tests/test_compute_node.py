@@ -197,3 +197,77 @@ def test_chain_failures_come_back_to_the_client(tmp_path):
         for s, _ in (a, b):
             s.shutdown()
             s.server_close()
+
+
+# ---- round 2: load metadata, restart of the production singleton, route validation -------------------
+def test_load_options_come_from_the_slice_metadata():
+    from distributedllm_b200.compute_node.slices import load_options
+    assert load_options({"type": "slice", "model": "m", "layer_from": 0, "layer_to": 3}) == {}
+    assert load_options({"n_ctx": 2048, "device": 3, "n_sessions": 8, "model": "m"}) == {"n_ctx": 2048, "device": 3, "n_sessions": 8}
+    assert load_options({"b200": {"n_ctx": "1024"}, "n_ctx": 512}) == {"n_ctx": 1024}          # the sub-object wins
+    assert load_options({"device": 0}) == {"device": 0}
+    for bad in ({"n_ctx": 0}, {"n_sessions": -1}, {"device": -2}):
+        with pytest.raises(ValueError):
+            load_options(bad)
+
+
+def test_slice_container_passes_load_options_to_the_llm_module(monkeypatch):
+    """routes.py hands the upload's metadata to SliceContainer.load; n_ctx / device / n_sessions reach llm.load_slice as
+    keyword extras (no process environment involved), and two loads may differ."""
+    import types
+
+    from distributedllm_b200.compute_node import slices
+    calls = []
+    fake = types.SimpleNamespace(load_slice=lambda path, **kw: calls.append((path, kw)) or 0, propagate_forward=None)
+    monkeypatch.setattr(slices, "import_llm", lambda: fake)
+    c = slices.SliceContainer(None)
+    c.load("/x/a.bin", {"type": "slice", "model": "m", "n_ctx": 2048, "n_sessions": 8})
+    c.load("/x/b.bin", {"type": "slice", "model": "m", "b200": {"n_ctx": 512, "device": 1}})
+    c.load("/x/c.bin", {"type": "slice", "model": "m"})
+    assert calls == [("/x/a.bin", {"n_ctx": 2048, "n_sessions": 8}), ("/x/b.bin", {"n_ctx": 512, "device": 1}), ("/x/c.bin", {})]
+
+
+def test_production_context_survives_a_restart_with_a_respelled_uploads_dir(tmp_path, monkeypatch):
+    """the singleton was keyed on registry.root, which restore_registry overwrites with the root stored in
+    registry_data.json -- a node restarted with './uploads' instead of 'uploads' lost every uploaded slice."""
+    import distributedllm_b200.compute_node.tcp_handler as th
+    monkeypatch.chdir(tmp_path)
+    th._PROD = None
+    ctx = RequestContext.production("uploads", ["a", "b"])
+    serve.restore_registry(ctx, "uploads")
+    _upload(ctx, bytes([2, 5]), {"type": "slice", "model": "m", "layer_from": 0, "layer_to": 3, "format": "test"})
+    assert ctx.registry.finished == [0]
+    # restart: fresh process state, the directory spelled differently
+    th._PROD = None
+    spelled = "./uploads"
+    ctx2 = RequestContext.production(spelled, ["a", "b"])
+    serve.restore_registry(ctx2, spelled)
+    assert RequestContext.production(spelled, ["a", "b"]) is ctx2            # the first request must NOT rebuild it
+    assert ctx2.registry.finished == [0] and ctx2.registry.next_id == 1
+    assert ctx2.registry.root == spelled
+    assert [s["name"] for s in json.loads(routes["slices_request"](ctx2, protocol.RequestAllSlices()).slices_json)] == ["a"]
+    sid, _ = _upload(ctx2, bytes([1, 1]), {"type": "slice", "model": "m", "layer_from": 4, "layer_to": 7, "format": "test"})
+    assert sid == 1                                                           # does not overwrite upload_0
+    th._PROD = None
+
+
+def test_route_is_validated_before_the_forward_runs():
+    from distributedllm_b200.compute_node import routes as R
+    ctx = RequestContext.default(names=["a"])
+    ctx.self_addresses = ("127.0.0.1:9000",)
+    ran = []
+    ctx.slice_container.forward = lambda t: ran.append(1) or t
+    data = b"\0" * 8
+
+    def ask(route):
+        return routes["propagate_bytes_request"](ctx, protocol.RequestPropagateBytes(1, 2, data, json.dumps(route)))
+    assert ask(["nonsense"]).error == "chain_hop_failed"
+    assert ask(["host:99999"]).error == "chain_hop_failed"
+    assert ask(["127.0.0.1:9000"]).error == "chain_hop_failed"                # loops back to this node
+    assert ask(["10.0.0.1:1"] * (R.MAX_ROUTE_HOPS + 1)).error == "chain_hop_failed"
+    assert ask({"not": "a list"}).error == "chain_hop_failed"
+    assert ran == []                                                          # nothing was computed for a bad route
+    ctx.peers = ("10.0.0.2:7000",)
+    assert ask(["10.0.0.3:7000"]).error == "chain_hop_failed"                 # not in the peer list
+    assert ran == []
+    assert ask([]).msg == "tensor_bytes_response" and ran == [1]

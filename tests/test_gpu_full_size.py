@@ -107,3 +107,33 @@ def test_config5_13b_batch_of_8_sessions(tmp_path):
     gpu.close()
     for r in refs:
         r.close()
+
+
+@needs_ref
+def test_config2_7b_q4_decode_at_the_end_of_the_sequence(tmp_path):
+    """The positions BASELINE's metric is quoted on: a 2-layer LLaMA-7B Q4_0 slice taken to p = 500 in prompt chunks,
+    then decoded token by token at p = 500..511 (T up to 512 in attention: every staged-row / tail path of the decode
+    kernels) -- hidden states bit-identical to the compiled reference at every step, including the chunked prefill."""
+    from distributedllm_b200 import capi
+    from oracle import oracle
+    sh = ggjt.SHAPES["7b"]
+    p = str(tmp_path / "q4_7b_2l.bin")
+    ggjt.write_fast_q4_slice(p, sh, 0, 1, seed=6)
+    gpu, ref = capi.Slice(p, 0, 512), oracle.RefSlice(p, THREADS, 512)
+    rng = np.random.default_rng(11)
+    pos, bad = 0, 0
+    while pos < 500:                                               # the reference's arena caps a call at ~64 tokens
+        n = min(oracle.RefSlice.MAX_CHUNK, 500 - pos)
+        x = rng.standard_normal((n, sh.n_embd), dtype=np.float32)
+        bad += int((_bits(gpu.forward(x)) != _bits(ref.forward(x))).sum())
+        pos += n
+    assert bad == 0, "%d floats differ in the chunked prefill" % bad
+    for pos in range(500, 512):
+        x = rng.standard_normal((1, sh.n_embd), dtype=np.float32)
+        g, r = gpu.forward(x), ref.forward(x)
+        assert (_bits(g) == _bits(r)).all(), "decode step at position %d differs" % pos
+    assert gpu.n_past == 512
+    with pytest.raises(capi.B200Error):                            # position 512 does not exist at n_ctx 512
+        gpu.forward(rng.standard_normal((1, sh.n_embd), dtype=np.float32))
+    gpu.close()
+    ref.close()

@@ -217,3 +217,82 @@ def test_llm_module_sessions(llm, tmp_models, monkeypatch):
             p.close()
     finally:
         llm.unload_slice()
+
+
+def test_node_loads_slices_with_different_n_ctx_from_metadata_without_env(llm, tmp_path, monkeypatch):
+    """n_ctx / n_sessions / device are LOAD METADATA carried by the slice's upload metadata through
+    routes.load_slice_request -> SliceContainer.load -> llm.load_slice(path, n_ctx=..., ...); no process environment."""
+    from distributedllm_b200.control_center import Connection
+    for v in ("B200_N_CTX", "B200_SESSIONS", "B200_DEVICE"):
+        monkeypatch.delenv(v, raising=False)
+    sh = ggjt.SHAPES["tiny128"]
+    p = str(tmp_path / "s.bin")
+    ggjt.write_synth_slice(p, sh, 0, 1, ggjt.T_Q4_0, seed=0)
+    srv = _serve(tmp_path)
+    try:
+        conn = Connection(("127.0.0.1", srv.server_address[1]))
+        names = []
+        for meta in ({"layer_from": 0, "layer_to": 1, "n_ctx": 96, "n_sessions": 3},
+                     {"layer_from": 0, "layer_to": 1, "b200": {"n_ctx": 160}}):
+            with open(p, "rb") as f:
+                names.append(conn.push_slice(f, "tiny128", meta)["file_name"])
+        conn.load_slice(names[0])
+        info = llm.slice_info()
+        assert (info["n_ctx"], info["n_sessions"], info["device"]) == (96, 3, 0)
+        x = np.zeros(97 * sh.n_embd, np.float32)
+        assert isinstance(llm.propagate_forward(x.tolist()), int)              # 97 tokens overflow n_ctx = 96
+        conn.load_slice(names[1])                                              # replaces the first slice (freed first)
+        info = llm.slice_info()
+        assert (info["n_ctx"], info["n_sessions"]) == (160, 1)
+        out = llm.propagate_forward(np.zeros(97 * sh.n_embd, np.float32).tolist())
+        assert isinstance(out, list) and len(out) == 97 * sh.n_embd
+    finally:
+        srv.shutdown()
+        srv.server_close()
+        llm.unload_slice()
+    assert llm.slice_info() is None
+
+
+def test_load_rejects_a_context_the_attention_kernels_cannot_hold(tmp_models):
+    from distributedllm_b200 import capi
+    path = tmp_models("tiny128", ggjt.T_Q4_0, 0, 1)
+    with pytest.raises(capi.B200Error) as ei:
+        capi.Slice(path, 0, 1 << 16)
+    assert ei.value.code == 1 and "n_ctx" in str(ei.value)                     # B200_EINVAL at load, not a launch error later
+    ok = capi.Slice(path, 0, 4096)
+    ok.close()
+
+
+def test_unload_racing_a_forward_is_safe(llm, tmp_models):
+    """the node is a ThreadingTCPServer -- an unload / reload arriving while another thread's
+    propagate_forward is on the GPU must neither crash nor free the slice under it."""
+    sh = ggjt.SHAPES["tiny128"]
+    path = tmp_models("tiny128", ggjt.T_Q4_0, 0, 2)
+    llm.load_slice(path, n_ctx=512)
+    stop, errors, done = threading.Event(), [], [0]
+
+    def hammer():
+        x = np.zeros((8, sh.n_embd), np.float32)
+        while not stop.is_set():
+            try:
+                llm.clear_context()
+                llm.propagate_forward_buffer(x)
+                done[0] += 1
+            except RuntimeError:
+                pass                                                        # "no slice loaded" between unload and load
+            except Exception as e:                                          # noqa: BLE001
+                errors.append(repr(e))
+                return
+    ts = [threading.Thread(target=hammer) for _ in range(3)]
+    for t in ts:
+        t.start()
+    try:
+        for i in range(12):
+            llm.unload_slice()
+            llm.load_slice(path, n_ctx=256 if i % 2 else 512)
+    finally:
+        stop.set()
+        for t in ts:
+            t.join()
+        llm.unload_slice()
+    assert not errors and done[0] > 0
