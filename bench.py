@@ -258,16 +258,12 @@ def run_b200(args):
     K, W = args.steps, args.warmup
     cycle = N_CTX - PREFILL
 
+    transport = None
     if world > 1:
         import torch
-        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            raw = np.zeros(128, np.uint8)
-            capi.check(capi.lib().b200_pipeline_unique_id(raw.ctypes.data))
-            idbuf.copy_(torch.from_numpy(raw))
-        dist.broadcast(idbuf, 0)
-        raw = idbuf.cpu().numpy().copy()
-        capi.check(capi.lib().b200_pipeline_init(sl.handle, rank, world, raw.ctypes.data))
+        from distributedllm_b200.pipeline import join_pipeline, torch_collectives
+        bcast, gather = torch_collectives(dist, torch.device("cuda", local))
+        transport = join_pipeline(sl, rank, world, bcast, gather, peer=os.environ.get("B200_PP_PEER", "1") != "0")
 
     def barrier():
         sl.sync()
@@ -551,7 +547,9 @@ def run_b200(args):
                            "weights": "synthetic Q4_0 blocks (seed %d), reference slice-file format" % SEED,
                            "mode": "exact (bit-identical to the reference CPU path)",
                            "slice_load_seconds": round(load_seconds, 3), "cuda_init_seconds": round(cuda_init_seconds, 3),
-                           "parallelism": "pp%d (layer slices, NCCL send/recv hand-off)" % world if world > 1 else "pp1",
+                           "parallelism": ("pp%d (layer slices; hand-off = %s)" % (world, "peer-memory store + flag over NVLink inside the step graph"
+                                                                    if transport == "peer" else "one ncclSend/ncclRecv per hop")) if world > 1 else "pp1",
+                           "handoff_transport": transport,
                            "l2": "no flush: each step streams %.2f GB of weights, 29x the 126 MB L2" % (W_all / 1e9),
                            "timing": "CUDA events on the slice's stream around %d steps; wall %.1f ms" % (K, wall_ms)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "step_roofline": step_roof,
@@ -559,6 +557,8 @@ def run_b200(args):
                 "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if capi.lib().b200_pipeline_error(sl.handle):
+            sys.stderr.write("rank %d: a mailbox poll timed out\n" % rank)
         capi.check(capi.lib().b200_pipeline_destroy(sl.handle))
         dist.barrier()
         dist.destroy_process_group()

@@ -1126,6 +1126,107 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     if (threadIdx.x == 0) B200_TRACE(a.trace, 3);
 }
 
+// =============================================================================================
+// Inter-slice hand-off through PEER MEMORY (NVLink / NVSwitch), no host and no NCCL kernel in the path.
+// Every rank owns a MAILBOX in its own HBM, mapped into its ring neighbours (cudaIpc):
+//     flag[kMbSlots]  written by the PREVIOUS rank: sequence number of the message sitting in inbox slot (seq & 1)
+//     ack             written by the NEXT rank: highest sequence number it has consumed from OUR sends
+//     inbox[kMbSlots][n_ctx * n_embd] f32
+// k_peer_send (last kernel of a slice's step) waits until its slot at the receiver is free, stores the activation
+// into the receiver's inbox over NVLink, fences at system scope and publishes the sequence number; k_peer_recv (first
+// kernel of the next slice's step) polls its local flag, copies the slot into the slice's input buffer and acknowledges.
+// Both live inside the step's captured graph with programmatic dependent launch: while k_peer_recv polls, the first
+// weight matmul of the slice is already resident and streaming its weights into shared memory.
+// Sequence counters are per link and live in device memory, so a graph replay needs no host-side argument.
+// A poll that exceeds kMbTimeoutNs sets *err and falls through (the host reports it) instead of hanging the GPU.
+// =============================================================================================
+constexpr int kMbSlots = 2;
+constexpr unsigned long long kMbTimeoutNs = 8000000000ull;
+
+struct MailboxHdr {              // first 256 bytes of a mailbox block
+    int flag[kMbSlots];          // remote-written (previous rank)
+    int pad0[14];
+    int ack;                     // remote-written (next rank)
+    int pad1[15];
+    int seq_in, seq_out;         // local counters
+    int err;                     // local: a poll timed out
+    int pad2[29];
+};
+static_assert(sizeof(MailboxHdr) == 256, "mailbox header layout");
+
+__device__ __forceinline__ int ld_acquire_sys(const int * p) {
+    int v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(int * p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+struct PeerRecvArgs {
+    MailboxHdr * mine;           // local mailbox
+    const float * inbox;         // local inbox base
+    size_t slot_floats;
+    int * peer_ack;              // &previous rank's mailbox->ack (remote)
+    float * dst; int count;      // floats to deliver into the slice's input buffer
+};
+
+__global__ void __launch_bounds__(1024) k_peer_recv(const PeerRecvArgs a) {
+    if (threadIdx.x == 0) grid_dep_launch();          // the slice's first matmul may start streaming its weights now
+    grid_dep_wait();                                  // everything before this step on the stream is done (dst is free)
+    __shared__ int s_seq;
+    if (threadIdx.x == 0) {
+        const int s = a.mine->seq_in + 1;
+        const unsigned long long t0 = gtime();
+        while (ld_acquire_sys(&a.mine->flag[s & (kMbSlots - 1)]) != s) {
+            if (gtime() - t0 > kMbTimeoutNs) { a.mine->err = 1; break; }
+        }
+        s_seq = s;
+    }
+    __syncthreads();
+    const int s = s_seq;
+    const float4 * src = (const float4 *)(a.inbox + (size_t)(s & (kMbSlots - 1)) * a.slot_floats);
+    float4 * dst = (float4 *) a.dst;
+    for (int i = threadIdx.x; i < a.count / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.mine->seq_in = s;
+        __threadfence_system();
+        st_release_sys(a.peer_ack, s);                // the sender may reuse this slot
+    }
+}
+
+struct PeerSendArgs {
+    MailboxHdr * mine;           // local mailbox (ack, seq_out)
+    MailboxHdr * peer;           // next rank's mailbox (remote): flag
+    float * peer_inbox;          // next rank's inbox base (remote)
+    size_t slot_floats;
+    const float * src; int count;
+};
+
+__global__ void __launch_bounds__(1024) k_peer_send(const PeerSendArgs a) {
+    if (threadIdx.x == 0) grid_dep_launch();
+    grid_dep_wait();                                  // src is the previous kernel's output
+    __shared__ int s_seq;
+    if (threadIdx.x == 0) {
+        const int s = a.mine->seq_out + 1;
+        const unsigned long long t0 = gtime();
+        while (ld_acquire_sys(&a.mine->ack) < s - kMbSlots) {      // message s - kMbSlots still occupies the slot
+            if (gtime() - t0 > kMbTimeoutNs) { a.mine->err = 1; break; }
+        }
+        s_seq = s;
+    }
+    __syncthreads();
+    const int s = s_seq;
+    float4 * dst = (float4 *)(a.peer_inbox + (size_t)(s & (kMbSlots - 1)) * a.slot_floats);
+    const float4 * src = (const float4 *) a.src;
+    for (int i = threadIdx.x; i < a.count / 4; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();                           // my stores are performed at the peer before the flag can be seen
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st_release_sys(&a.peer->flag[s & (kMbSlots - 1)], s);
+        a.mine->seq_out = s;
+    }
+}
+
 // position counter kept on the device so a captured graph can be replayed for every token
 __global__ void k_advance(int * n_past, int by) { grid_dep_wait(); if (threadIdx.x == 0) *n_past += by; }
 // batched step: every listed session moves one position

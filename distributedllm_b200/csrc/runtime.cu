@@ -5,6 +5,7 @@
 // one B200.  One stream per slice; the N=1 decode step is a CUDA graph replayed per token with
 // the position kept in device memory.
 #include "kernels.cuh"
+#include "persist.cuh"
 #include "fastgemm.cuh"
 #include "ggjt_file.hpp"
 
@@ -27,6 +28,7 @@ constexpr int kSmemLimit = 226 * 1024;   // opt-in dynamic limit is 227 KB minus
 
 struct LayerW {
     PackedW qkv{}, wo{}, w13{}, w2{};
+    PackedW wo_p{}, w2_p{};      // persistent-kernel copies of the narrow matrices with fewer row-groups per tile (B200_PERSIST_TR)
     // F16-weight slices
     uint16_t * f_q = nullptr, * f_k = nullptr, * f_v = nullptr, * f_o = nullptr, * f_1 = nullptr, * f_2 = nullptr, * f_3 = nullptr;
     float * attn_norm = nullptr, * ffn_norm = nullptr;
@@ -76,6 +78,14 @@ struct b200_slice {
     unsigned long long * trace = nullptr; int trace_next = 0; std::vector<int> trace_cls, trace_ctas;
     // layer-slice pipeline over NCCL (see b200_pipeline_*)
     void * nccl_comm = nullptr; int pp_rank = 0, pp_world = 1; float * d_final = nullptr;
+    // peer-memory hand-off (b200_pipeline_mailbox_*): my mailbox, and my ring neighbours' mailboxes mapped over NVLink
+    uint8_t * mb_block = nullptr; size_t mb_slot_floats = 0;
+    uint8_t * mb_next = nullptr, * mb_prev = nullptr; bool mb_on = false;
+    bool send_pending = false; PeerSendArgs send_args{};      // enqueue_layers launches the send right behind the last matmul
+    std::map<GraphKey, cudaGraphExec_t> pp_graphs;
+    // persistent single-token step (persist.cuh)
+    bool use_persist = false; int persist_tr = 4, persist_ns = 0, persist_ctas = 0;
+    int * p_cnt = nullptr; std::map<GraphKey, PLayer *> p_tables; unsigned long long * p_trace = nullptr;
 };
 
 namespace b200 {
@@ -241,12 +251,102 @@ static int launch_fast_gemm(b200_slice * s, const PackedW & W, const float * res
     return launch_simple(s, kern, dim3((groups + 15) / 16, (N + kFgN - 1) / kFgN, 1), dim3(160, 1, 1), kFgSmem, a);
 }
 
+// ---------------------------------------------------------------- persistent single-token step (persist.cuh)
+static bool persist_applicable(const b200_slice * s, int N) {
+    return s->use_persist && N == 1 && !s->cols && s->D == 128 && (s->wtype == kWT_Q4_0 || s->wtype == kWT_Q8_0) && !s->skip_attention &&
+           !s->profiling && s->E / 32 <= kPConsumers && s->p_cnt != nullptr;
+}
+
+static PMat pmat_of(const PackedW & W, int G) {
+    PMat m{};
+    m.data = W.data; m.n_tiles = W.n_tiles; m.nbq = W.nbq; m.TR = W.TR; m.tile_bytes = W.tile_bytes;
+    int sq = 16 / W.TR;                       // quads per stage: sq * TR * chunk <= slot (16 chunks)
+    while (sq > 1 && W.nbq % sq) sq >>= 1;
+    m.sq = sq; (void) G;
+    return m;
+}
+
+// The layer table of a step (weights + this call's buffers) lives in device memory; it depends on (in, out, session), so
+// it is built once per such triple -- OUTSIDE any stream capture, which is why forward paths call this before capturing.
+static int persist_prepare(b200_slice * s, const float * in, float * out) {
+    GraphKey key{in, out, s->cur};
+    if (s->p_tables.count(key)) return 0;
+    std::vector<PLayer> tab(s->L);
+    const float * cur = in;
+    const int E = s->E;
+    const size_t sess_off = (size_t) s->cur * s->sess_stride;
+    for (int il = 0; il < s->L; il++) {
+        LayerW & Lw = s->layers[il];
+        PLayer & P = tab[il];
+        P.qkv = pmat_of(Lw.qkv, 1);
+        P.wo = pmat_of(Lw.wo_p.data ? Lw.wo_p : Lw.wo, 1);
+        P.w13 = pmat_of(Lw.w13, 2);
+        P.w2 = pmat_of(Lw.w2_p.data ? Lw.w2_p : Lw.w2, 1);
+        P.attn_norm = Lw.attn_norm; P.ffn_norm = Lw.ffn_norm;
+        float * nxt = (il == s->L - 1) ? out : ((il & 1) ? s->xb : s->xa);
+        P.x_in = cur; P.x_out = nxt;
+        P.kc = s->kc + sess_off + (size_t) il * s->n_ctx * E; P.vc = s->vc + sess_off + (size_t) il * s->n_ctx * E;
+        cur = nxt;
+    }
+    PLayer * d = nullptr;
+    int rc = dev_alloc(s, &d, (size_t) s->L);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpy(d, tab.data(), tab.size() * sizeof(PLayer), cudaMemcpyHostToDevice));
+    s->p_tables[key] = d;
+    return 0;
+}
+
+static int launch_persistent(b200_slice * s, const float * in, float * out) {
+    auto it = s->p_tables.find(GraphKey{in, out, s->cur});
+    if (it == s->p_tables.end()) return fail(B200_EINVAL, "persistent step: layer table not prepared");
+    PersistArgs a{};
+    a.layers = it->second; a.L = s->L;
+    a.E = s->E; a.FF = s->FF; a.H = s->H; a.n_ctx = s->n_ctx; a.nb_E = s->E / 32; a.nbqE = s->nbqE; a.nbqF = s->nbqF;
+    a.n_past = s->d_npast + s->cur;
+    a.qkv = s->qkv; a.att = s->att; a.ffin = s->ffin;
+    a.aq_att = s->aq_att; a.da_att = s->da_att; a.aq_gate = s->aq_gate; a.da_gate = s->da_gate;
+    a.dscale = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
+    a.cs = s->cs; a.texp = s->texp; a.tsilu = s->tsilu;
+    a.cnt = s->p_cnt;
+    a.kq_scale = 1.0f / sqrtf((float) s->E / (float) s->H);
+    a.trace = s->p_trace;
+    const int nbq_max = s->nbqF > s->nbqE ? s->nbqF : s->nbqE;
+    const size_t limit = 227 * 1024;
+    int NS = s->persist_ns > 0 ? s->persist_ns : 8;
+    while (NS > 2 && p_smem_layout(s->wtype, NS, nbq_max, s->E, s->n_ctx).total > limit) NS--;
+    const PSmem lay = p_smem_layout(s->wtype, NS, nbq_max, s->E, s->n_ctx);
+    if (lay.total > limit) return fail(B200_EINVAL, "persistent step needs %zu B of shared memory", lay.total);
+    a.NS = NS;
+    static bool attr_set[16] = {false};
+    if (!attr_set[s->device & 15]) {
+        B200_CUDA(cudaFuncSetAttribute(k_decode_persistent<kWT_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit));
+        B200_CUDA(cudaFuncSetAttribute(k_decode_persistent<kWT_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) limit));
+        attr_set[s->device & 15] = true;
+    }
+    // progress counters start at zero every step
+    B200_CUDA(cudaMemsetAsync(s->p_cnt, 0, (size_t) s->L * kPPhases * 4, s->stream));
+    int grid = s->persist_ctas > 0 ? s->persist_ctas : s->n_sm;      // one CTA per SM, all co-resident (they wait on each other)
+    if (grid > s->n_sm) grid = s->n_sm;
+    if (grid < s->H) return fail(B200_EINVAL, "persistent step needs at least n_head (%d) CTAs", s->H);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(kPThreads, 1, 1); cfg.dynamicSmemBytes = lay.total; cfg.stream = s->stream;
+    s->cur_class = 0;
+    prof_begin(s);
+    if (s->wtype == kWT_Q4_0) B200_CUDA(cudaLaunchKernelEx(&cfg, k_decode_persistent<kWT_Q4_0>, a));
+    else                      B200_CUDA(cudaLaunchKernelEx(&cfg, k_decode_persistent<kWT_Q8_0>, a));
+    prof_end(s);
+    s->launches++;
+    return 0;
+}
+
 // ---------------------------------------------------------------- one forward over the slice
 // Enqueue every layer for N tokens at device-side position *d_npast (tensor_processor.cpp:537-766).
 static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) {
     const int E = s->E, FF = s->FF, H = s->H, D = s->D;
     const float * cur = in;
-    for (int il = 0; il < s->L; il++) {
+    const bool persist = persist_applicable(s, N);
+    if (persist) { int rc = launch_persistent(s, in, out); if (rc) return rc; }
+    for (int il = 0; il < (persist ? 0 : s->L); il++) {
         LayerW & Lw = s->layers[il];
         // grid-barrier norm+quant epilogue: decode only (every CTA of wo / w2 must be co-resident: 1 tile per CTA)
         const bool fast = s->fast_prefill && N >= s->fast_min_tokens && s->wtype == kWT_Q4_0 && (Lw.qkv.n_tiles * Lw.qkv.TR) % 16 == 0 &&
@@ -389,6 +489,13 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         }
         cur = nxt;
     }
+    if (s->send_pending) {
+        // pipeline hand-off: the activation leaves for the next slice's GPU right behind the last matmul
+        s->send_pending = false;
+        s->cur_class = 6;
+        int rc = launch_simple(s, k_peer_send, dim3(1, 1, 1), dim3(1024, 1, 1), 0, s->send_args);
+        if (rc) return rc;
+    }
     {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.stream = s->stream;
@@ -408,9 +515,10 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
 
 // N = 1: replay a captured graph (host variant adds the H2D / D2H copies as graph nodes)
 static int run_decode_graph(b200_slice * s, const float * in, float * out, bool host) {
-    GraphKey key{in, out, (host ? 1 : 0) | (s->skip_attention ? 2 : 0) | (s->cur << 2)};
+    GraphKey key{in, out, (host ? 1 : 0) | (s->skip_attention ? 2 : 0) | (s->send_pending ? 4 : 0) | (s->cur << 3)};
     auto it = s->graphs.find(key);
-    const int per_step = (s->D == 128 ? 5 : 6) * s->L + 1;
+    const int per_step = persist_applicable(s, 1) ? 2 : (s->D == 128 ? 5 : 6) * s->L + 1;
+    if (persist_applicable(s, 1)) { int rc = persist_prepare(s, host ? s->d_in : in, host ? s->d_out : out); if (rc) return rc; }
     if (it == s->graphs.end()) {
         const int64_t before = s->launches;
         cudaGraph_t g = nullptr;
@@ -466,6 +574,7 @@ static int forward_locked(b200_slice * s, const float * in, int N, float * out, 
             memcpy(out, s->h_out, (size_t) s->E * 4);
         } else {
             B200_CUDA(cudaMemcpyAsync(s->d_in, in, (size_t) N * s->E * 4, cudaMemcpyHostToDevice, s->stream));
+            if (persist_applicable(s, N) && (rc = persist_prepare(s, s->d_in, s->d_out))) return rc;
             if ((rc = enqueue_layers(s, s->d_in, N, s->d_out))) return rc;
             B200_CUDA(cudaEventRecord(s->ev1, s->stream));
             B200_CUDA(cudaMemcpyAsync(out, s->d_out, (size_t) N * s->E * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -473,7 +582,10 @@ static int forward_locked(b200_slice * s, const float * in, int N, float * out, 
         }
     } else {
         if (N == 1 && s->use_graph && !s->profiling) { if ((rc = run_decode_graph(s, in, out, false))) return rc; }
-        else if ((rc = enqueue_layers(s, in, N, out))) return rc;
+        else {
+            if (persist_applicable(s, N) && (rc = persist_prepare(s, in, out))) return rc;
+            if ((rc = enqueue_layers(s, in, N, out))) return rc;
+        }
         B200_CUDA(cudaEventRecord(s->ev1, s->stream));
     }
     s->timed = true;
@@ -532,6 +644,7 @@ struct LoadJob {
     int kind = 0;                 // 0: block-quantised matrix (k_repack), 1: F16 (k_repack_f16), 2: raw copy, 3: Q6_K (k_repack_q6k)
     int mode = 0, G = 1;
     PackedW * out = nullptr;      // kind 0
+    PackedW * out2 = nullptr; int TR2 = 0;   // kind 0: a second packing of the same matrix with TR2 row-groups per tile
     uint16_t ** outf = nullptr; uint16_t * into = nullptr;   // kind 1
     uint8_t * raw_dst = nullptr;  // kind 2
     size_t bytes() const { size_t n = 0; for (int i = 0; i < nsrc; i++) n += (src[i]->nbytes + 255) & ~(size_t) 255; return n; }
@@ -562,7 +675,7 @@ static int run_load_jobs(b200_slice * s, const GgjtFile & f, std::vector<LoadJob
         B200_CUDA(cudaMalloc((void **) &lp.scratch[i], lp.slot_bytes));
         B200_CUDA(cudaEventCreateWithFlags(&lp.ev[i], cudaEventDisableTiming));
     }
-    madvise((void *) f.base, f.size, MADV_WILLNEED);       // start the kernel's read-ahead for a cold file
+    posix_fadvise(f.fd, 0, 0, POSIX_FADV_SEQUENTIAL);       // a cold file: deep kernel read-ahead in front of the preads
     std::mutex mu; std::condition_variable cv;
     size_t filled = 0, consumed = 0; bool abort_flag = false;
     const int device = s->device;
@@ -576,11 +689,31 @@ static int run_load_jobs(b200_slice * s, const GgjtFile & f, std::vector<LoadJob
                 if (abort_flag) return;
             }
             if (j >= LoadPipe::NB) cudaEventSynchronize(lp.ev[slot]);    // the slot's previous repack has read its scratch
+            // pread straight into the pinned slot: page-cache copy without the per-4-KiB minor faults a private file
+            // mapping costs; the job is cut in two so a second thread overlaps its copy
+            struct Piece { uint8_t * dst; size_t off, n; };
+            std::vector<Piece> pieces;
             size_t off = 0;
             for (int i = 0; i < jobs[j].nsrc; i++) {
-                memcpy(lp.pinned[slot] + off, f.data(*jobs[j].src[i]), jobs[j].src[i]->nbytes);
-                off += (jobs[j].src[i]->nbytes + 255) & ~(size_t) 255;
+                const GgjtTensor & t = *jobs[j].src[i];
+                const size_t half = (t.nbytes / 2) & ~(size_t) 4095;
+                pieces.push_back({lp.pinned[slot] + off, t.offset, half});
+                pieces.push_back({lp.pinned[slot] + off + half, t.offset + half, t.nbytes - half});
+                off += (t.nbytes + 255) & ~(size_t) 255;
             }
+            auto pull = [&](int first) {
+                for (size_t k = first; k < pieces.size(); k += 2) {
+                    size_t done = 0;
+                    while (done < pieces[k].n) {
+                        const ssize_t got = pread(f.fd, pieces[k].dst + done, pieces[k].n - done, (off_t)(pieces[k].off + done));
+                        if (got <= 0) { memcpy(pieces[k].dst + done, f.base + pieces[k].off + done, pieces[k].n - done); break; }
+                        done += (size_t) got;
+                    }
+                }
+            };
+            std::thread helper(pull, 1);
+            pull(0);
+            helper.join();
             { std::lock_guard<std::mutex> lk(mu); filled = j + 1; }
             cv.notify_all();
         }
@@ -610,6 +743,18 @@ static int run_load_jobs(b200_slice * s, const GgjtFile & f, std::vector<LoadJob
             PackedW * out = job.out;
             out->data = dst; out->wtype = wt; out->rows = rows_per * job.nsrc; out->K = K; out->nb = nb; out->nbq = nbq; out->TR = TR;
             out->n_tiles = n_tiles; out->tile_bytes = tile_bytes;
+            if (job.out2 && job.TR2 > 0) {
+                const int TR2 = job.TR2, n_tiles2 = (total_groups + TR2 - 1) / TR2;
+                // quads per ring stage of the persistent kernel: sq * TR2 <= 16; pad nbq so a whole number of stages fits
+                int sq = 16 / TR2; while (sq > 4 && nbq % sq) sq >>= 1;
+                const long long tile_bytes2 = (long long) nbq * TR2 * chunk_bytes(wt);
+                uint8_t * dst2 = nullptr;
+                if ((rc = dev_alloc(s, &dst2, (size_t) n_tiles2 * tile_bytes2))) break;
+                ra.TR = TR2; ra.n_tiles = n_tiles2; ra.dst = dst2;
+                k_repack<<<s->n_sm * 8, 256, 0, s->stream>>>(ra);
+                PackedW * o2 = job.out2;
+                *o2 = *out; o2->data = dst2; o2->TR = TR2; o2->n_tiles = n_tiles2; o2->tile_bytes = tile_bytes2;
+            }
         } else if (job.kind == 1) {
             const GgjtTensor & t = *job.src[0];
             const int K = (int) t.ne[0], rows = (int) t.ne[1];
@@ -667,10 +812,15 @@ static int build_tables(b200_slice * s) {
 }
 
 static int load_locked(b200_slice * s, const char * path) {
+    const bool ltrace = env_int("B200_LOAD_TRACE", 0) != 0;
+    auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = tnow(); double t_last = t_begin;
+    auto lap = [&](const char * what) { if (ltrace) { const double t = tnow(); fprintf(stderr, "[b200 load] %-28s %7.3f s\n", what, t - t_last); t_last = t; } };
     std::unique_ptr<GgjtFile> fp;
     try { fp.reset(new GgjtFile(path, false)); }
     catch (const std::exception & e) { return fail(B200_EFILE, "error loading model: %s", e.what()); }
     GgjtFile & f = *fp;
+    lap("parse header + tensor index");
     if (f.n_layer == 0 || f.n_head == 0 || f.n_embd % f.n_head || f.n_embd % 32)
         return fail(B200_EFILE, "not a transformer slice file (n_layer=%u n_embd=%u n_head=%u)", f.n_layer, f.n_embd, f.n_head);
     s->E = (int) f.n_embd; s->H = (int) f.n_head; s->D = s->E / s->H; s->L = (int) f.n_layer; s->first_layer = (int) f.first_layer;
@@ -732,9 +882,13 @@ static int load_locked(b200_slice * s, const char * path) {
                 }
             } else {
                 LoadJob a; a.nsrc = 3; a.src[0] = &wq; a.src[1] = &wk; a.src[2] = &wv; a.mode = 1; a.G = 1; a.out = &Lw.qkv; jobs.push_back(a);
-                LoadJob o; o.nsrc = 1; o.src[0] = &wo; o.mode = 0; o.G = 1; o.out = &Lw.wo; jobs.push_back(o);
+                LoadJob o; o.nsrc = 1; o.src[0] = &wo; o.mode = 0; o.G = 1; o.out = &Lw.wo;
+                if (s->use_persist && s->persist_tr != 4) { o.out2 = &Lw.wo_p; o.TR2 = s->persist_tr; }
+                jobs.push_back(o);
                 LoadJob g; g.nsrc = 2; g.src[0] = &w1; g.src[1] = &w3; g.mode = 2; g.G = 2; g.out = &Lw.w13; jobs.push_back(g);
-                LoadJob d; d.nsrc = 1; d.src[0] = &w2; d.mode = 0; d.G = 1; d.out = &Lw.w2; jobs.push_back(d);
+                LoadJob d; d.nsrc = 1; d.src[0] = &w2; d.mode = 0; d.G = 1; d.out = &Lw.w2;
+                if (s->use_persist && s->persist_tr != 4) { d.out2 = &Lw.w2_p; d.TR2 = s->persist_tr; }
+                jobs.push_back(d);
             }
             s->weight_bytes += (int64_t)(an.nbytes + fn.nbytes + wq.nbytes + wk.nbytes + wv.nbytes + wo.nbytes + w1.nbytes + w2.nbytes + w3.nbytes);
         }
@@ -743,6 +897,7 @@ static int load_locked(b200_slice * s, const char * path) {
     } catch (const std::exception & e) {
         return fail(B200_EFILE, "error loading model: %s", e.what());
     }
+    lap("weights: read + upload + repack");
 
     const size_t nE = (size_t) s->n_ctx * E;
     s->sess_stride = (size_t) s->L * nE;
@@ -762,6 +917,8 @@ static int load_locked(b200_slice * s, const char * path) {
             (rc = dev_alloc(s, &s->aq_gate, nq * s->nbqF * 32)) || (rc = dev_alloc(s, &s->da_gate, nq * s->nbqF * 4))) return rc;
         if ((rc = dev_alloc(s, &s->aq_x, nq * s->nbqE * 32)) || (rc = dev_alloc(s, &s->da_x, nq * s->nbqE * 4)) ||
             (rc = dev_alloc(s, &s->nq_counter, 2 * nq)) || (rc = dev_alloc(s, &s->nq_partial, nq * 256))) return rc;
+        if ((rc = dev_alloc(s, &s->p_cnt, (size_t) s->L * kPPhases + 32))) return rc;
+        B200_CUDA(cudaMemset(s->p_cnt, 0, ((size_t) s->L * kPPhases + 32) * 4));
         B200_CUDA(cudaMemset(s->aq_x, 0, nq * s->nbqE * 128)); B200_CUDA(cudaMemset(s->da_x, 0, nq * s->nbqE * 16));
         B200_CUDA(cudaMemset(s->nq_counter, 0, 2 * nq * 4));
         B200_CUDA(cudaMemset(s->aq_att, 0, nq * s->nbqE * 128));  B200_CUDA(cudaMemset(s->da_att, 0, nq * s->nbqE * 16));
@@ -772,7 +929,9 @@ static int load_locked(b200_slice * s, const char * path) {
     B200_CUDA(cudaMemset(s->d_npast, 0, 4 * (size_t) s->n_sessions));
     B200_CUDA(cudaMallocHost((void **) &s->h_in, (size_t) E * 4));
     B200_CUDA(cudaMallocHost((void **) &s->h_out, (size_t) E * 4));
+    lap("KV cache + activations");
     if ((rc = build_tables(s))) return rc;
+    lap("exp / SiLU / RoPE tables");
     if (env_int("B200_TRACE", 0)) {
         if ((rc = dev_alloc(s, &s->trace, (size_t) 512 * 1024 * 8))) return rc;
         B200_CUDA(cudaMemset(s->trace, 0, (size_t) 512 * 1024 * 8 * 8));
@@ -783,6 +942,8 @@ static int load_locked(b200_slice * s, const char * path) {
     B200_CUDA(cudaEventCreate(&s->ev0));
     B200_CUDA(cudaEventCreate(&s->ev1));
     B200_CUDA(cudaDeviceSynchronize());
+    lap("attributes + final sync");
+    if (ltrace) fprintf(stderr, "[b200 load] total %.3f s for %.2f GB of weights\n", tnow() - t_begin, s->weight_bytes / 1e9);
     return 0;
 }
 
@@ -790,6 +951,9 @@ static void destroy(b200_slice * s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto & kv : s->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto & kv : s->pp_graphs) cudaGraphExecDestroy(kv.second);
+    if (s->mb_next) cudaIpcCloseMemHandle(s->mb_next);
+    if (s->mb_prev && s->mb_prev != s->mb_next) cudaIpcCloseMemHandle(s->mb_prev);
     for (void * p : s->allocs) cudaFree(p);
     if (s->h_in) cudaFreeHost(s->h_in);
     if (s->h_out) cudaFreeHost(s->h_out);
@@ -836,6 +1000,9 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
     s->opt_ns = env_int("B200_NS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
     s->opt_pre = env_int("B200_PRE", 3); s->opt_nomath = env_int("B200_DBG_NOMATH", 0);
+    s->use_persist = env_int("B200_PERSIST", 0) != 0;         // single-token step as ONE persistent kernel (persist.cuh)
+    s->persist_tr = env_int("B200_PERSIST_TR", 4); s->persist_ns = env_int("B200_PERSIST_NS", 0); s->persist_ctas = env_int("B200_PERSIST_CTAS", 0);
+    if (s->persist_tr != 1 && s->persist_tr != 2 && s->persist_tr != 4) s->persist_tr = 4;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
     int rc = load_locked(s, path);
@@ -1169,6 +1336,78 @@ int b200_pipeline_init(b200_slice_t * s, int rank, int nranks, const void * id12
     return 0;
 }
 
+// Peer-memory variant of a pipeline step (see kernels.cuh, "Inter-slice hand-off through PEER MEMORY"): the hop is a
+// store into the next rank's mailbox + a flag, issued by k_peer_send right behind this slice's last matmul and picked
+// up by k_peer_recv in front of the next slice's first matmul.  For a single-token step the whole sequence
+// [recv ->] layers -> send [-> recv of the ring result] is ONE captured graph per rank: no host code between slices.
+static int pipeline_step_peer(b200_slice * s, const float * d_in, int n_rows, int ring, int session, const int * sessions) {
+    const int r = s->pp_rank, W = s->pp_world;
+    const size_t count = (size_t) n_rows * s->E;
+    if (count > s->mb_slot_floats) return fail(B200_EINVAL, "hand-off of %zu floats exceeds the mailbox slot (%zu)", count, s->mb_slot_floats);
+    const bool recv_in = r > 0, sends = r < W - 1 || ring, recv_final = r == 0 && ring;
+    MailboxHdr * mine = (MailboxHdr *) s->mb_block;
+    const float * inbox = (const float *)(s->mb_block + sizeof(MailboxHdr));
+    PeerRecvArgs ra{mine, inbox, s->mb_slot_floats, &((MailboxHdr *) s->mb_prev)->ack, s->d_in, (int) count};
+    PeerRecvArgs rf = ra; rf.dst = s->d_final;
+    PeerSendArgs sa{mine, (MailboxHdr *) s->mb_next, (float *)(s->mb_next + sizeof(MailboxHdr)), s->mb_slot_floats, s->d_out, (int) count};
+    const float * in = recv_in ? s->d_in : d_in;
+    int rc = 0;
+    if (!sessions) { s->cur = session; s->cols = nullptr; if (persist_applicable(s, n_rows) && (rc = persist_prepare(s, in, s->d_out))) return rc; }
+    auto body = [&]() -> int {
+        int e;
+        s->cur_class = 6;
+        if (recv_in && (e = launch_simple(s, k_peer_recv, dim3(1, 1, 1), dim3(1024, 1, 1), 0, ra))) return e;
+        if (sends) { s->send_args = sa; s->send_pending = true; }
+        e = enqueue_layers(s, in, n_rows, s->d_out);
+        s->send_pending = false;
+        if (e) return e;
+        s->cur_class = 6;
+        if (recv_final && (e = launch_simple(s, k_peer_recv, dim3(1, 1, 1), dim3(1024, 1, 1), 0, rf))) return e;
+        return 0;
+    };
+    B200_CUDA(cudaEventRecord(s->ev0, s->stream));
+    if (sessions) {
+        std::vector<int2> cols(n_rows);
+        for (int b = 0; b < n_rows; b++) cols[b] = make_int2(sessions[b], s->past[sessions[b]]);
+        B200_CUDA(cudaMemcpyAsync(s->d_cols, cols.data(), (size_t) n_rows * sizeof(int2), cudaMemcpyHostToDevice, s->stream));
+        s->cur = 0; s->cols = s->d_cols;
+        rc = body();
+        s->cols = nullptr;
+        if (rc) return rc;
+        for (int b = 0; b < n_rows; b++) s->past[sessions[b]] += 1;
+    } else if (n_rows == 1 && s->use_graph && !s->profiling) {
+        s->cur = session; s->cols = nullptr;
+        GraphKey key{in, nullptr, (ring ? 1 : 0) | (session << 1)};
+        auto it = s->pp_graphs.find(key);
+        if (it == s->pp_graphs.end()) {
+            const int64_t before = s->launches;
+            cudaGraph_t g = nullptr;
+            B200_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            rc = body();
+            cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+            s->launches = before;
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return fail(B200_ECUDA, "pipeline graph capture failed: %s", cudaGetErrorString(e));
+            cudaGraphExec_t ge = nullptr;
+            e = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(B200_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+            if (s->pp_graphs.size() >= 64) { for (auto & kv : s->pp_graphs) cudaGraphExecDestroy(kv.second); s->pp_graphs.clear(); }
+            it = s->pp_graphs.emplace(key, ge).first;
+        }
+        B200_CUDA(cudaGraphLaunch(it->second, s->stream));
+        s->launches += (persist_applicable(s, 1) ? 2 : (s->D == 128 ? 5 : 6) * s->L + 1) + (recv_in ? 1 : 0) + (sends ? 1 : 0) + (recv_final ? 1 : 0);
+        s->past[session] += 1;
+    } else {
+        s->cur = session; s->cols = nullptr;
+        if ((rc = body())) return rc;
+        s->past[session] += n_rows;
+    }
+    B200_CUDA(cudaEventRecord(s->ev1, s->stream));
+    s->timed = true;
+    return 0;
+}
+
 // recv <- rank-1, the slice's layers, send -> rank+1 (ring: the last rank hands its output back to rank 0).
 // sessions == nullptr: n_rows tokens of session `session`; else one token for each of the n_rows listed sessions.
 static int pipeline_step_locked(b200_slice * s, const float * d_in, int n_rows, int ring, int session, const int * sessions) {
@@ -1195,11 +1434,12 @@ static int pipeline_step_locked(b200_slice * s, const float * d_in, int n_rows, 
             return fail(B200_ECONTEXT, "context overflow: n_past %d + n_tokens %d > n_ctx %d", s->past[session], n_rows, s->n_ctx);
     }
     if (r == 0 && !d_in) return fail(B200_EINVAL, "rank 0 needs an input buffer");
+    if (s->mb_on && W > 1) return pipeline_step_peer(s, d_in, n_rows, ring, session, sessions);
     const float * in = d_in;
     if (r > 0) {
         if ((rc = n.Recv(s->d_in, count, kNcclFloat32, r - 1, s->nccl_comm, s->stream))) return nccl_fail("ncclRecv", rc);
         in = s->d_in;
-    } else if (!in) return fail(B200_EINVAL, "rank 0 needs an input buffer");
+    }
     if (sessions) rc = batch_locked(s, sessions, n_rows, in, s->d_out, false);
     else          rc = forward_locked(s, in, n_rows, s->d_out, false, session);
     if (rc) return rc;
@@ -1235,6 +1475,75 @@ int b200_pipeline_step_batch(b200_slice_t * s, const int * sessions, int n_seq, 
     return pipeline_step_locked(s, d_in, n_seq, ring, 0, sessions);
 }
 
+/* ---- peer-memory hand-off: mailboxes mapped across processes with cudaIpc --------------------------------------- */
+int b200_pipeline_mailbox_export(b200_slice_t * s, void * handle64) {
+    if (!s || !handle64) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    B200_CUDA(cudaSetDevice(s->device));
+    if (!s->mb_block) {
+        s->mb_slot_floats = (size_t) s->n_ctx * s->E;
+        const size_t bytes = sizeof(MailboxHdr) + (size_t) kMbSlots * s->mb_slot_floats * 4;
+        void * p = nullptr;
+        B200_CUDA(cudaMalloc(&p, bytes));                 // a dedicated cudaMalloc block: IPC handles cover whole allocations
+        s->allocs.push_back(p);
+        s->mb_block = (uint8_t *) p;
+        B200_CUDA(cudaMemset(p, 0, sizeof(MailboxHdr)));
+        B200_CUDA(cudaDeviceSynchronize());
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    B200_CUDA(cudaIpcGetMemHandle(&h, s->mb_block));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int b200_pipeline_mailbox_connect(b200_slice_t * s, const void * handles, int nranks) {
+    if (!s || !handles) return fail(B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->mb_block) return fail(B200_EINVAL, "export this rank's mailbox first");
+    if (nranks != s->pp_world || nranks < 2) return fail(B200_EINVAL, "mailbox_connect: %d handles for a pipeline of %d ranks", nranks, s->pp_world);
+    if (env_int("B200_PP_PEER", 1) == 0) { s->mb_on = false; return 0; }       // keep the NCCL send/recv path (tested fallback)
+    B200_CUDA(cudaSetDevice(s->device));
+    const int next = (s->pp_rank + 1) % nranks, prev = (s->pp_rank + nranks - 1) % nranks;
+    cudaIpcMemHandle_t hn, hp;
+    memcpy(&hn, (const uint8_t *) handles + (size_t) next * 64, 64);
+    memcpy(&hp, (const uint8_t *) handles + (size_t) prev * 64, 64);
+    void * pn = nullptr, * pp = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&pn, hn, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200_ECUDA, "cudaIpcOpenMemHandle(next rank %d) failed: %s", next, cudaGetErrorString(e)); }
+    if (prev == next) pp = pn;
+    else {
+        e = cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); cudaIpcCloseMemHandle(pn); return fail(B200_ECUDA, "cudaIpcOpenMemHandle(previous rank %d) failed: %s", prev, cudaGetErrorString(e)); }
+    }
+    s->mb_next = (uint8_t *) pn; s->mb_prev = (uint8_t *) pp;
+    s->mb_on = true;
+    return 0;
+}
+
+/* 1 when steps use the peer-memory mailboxes, 0 when they use ncclSend / ncclRecv. */
+int b200_pipeline_transport(b200_slice_t * s) { return s && s->mb_on ? 1 : 0; }
+
+/* Force the transport: 0 = NCCL (every rank must do the same, e.g. when ONE rank failed to map a neighbour),
+ * 1 = peer mailboxes (only valid after a successful connect). */
+int b200_pipeline_set_transport(b200_slice_t * s, int peer) {
+    if (!s) return fail(B200_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (peer && !(s->mb_next && s->mb_prev)) return fail(B200_EINVAL, "peer transport needs connected mailboxes");
+    s->mb_on = peer != 0;
+    return 0;
+}
+
+/* Non-zero if a mailbox poll timed out on this rank since the pipeline was connected (synchronises the stream). */
+int b200_pipeline_error(b200_slice_t * s) {
+    if (!s || !s->mb_block) return 0;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    int err = 0;
+    cudaMemcpy(&err, s->mb_block + offsetof(MailboxHdr, err), 4, cudaMemcpyDeviceToHost);
+    return err;
+}
+
 /* Device pointer of the pipeline's final activation on rank 0 (valid after a `ring` step), else dev_out. */
 float * b200_pipeline_result(b200_slice_t * s) { return s ? (s->pp_world > 1 && s->pp_rank == 0 && s->d_final ? s->d_final : s->d_out) : nullptr; }
 
@@ -1247,6 +1556,11 @@ int b200_pipeline_destroy(b200_slice_t * s) {
         NcclApi & n = nccl();
         if (n.CommDestroy) n.CommDestroy(s->nccl_comm);
         s->nccl_comm = nullptr; s->pp_world = 1; s->pp_rank = 0;
+        for (auto & kv : s->pp_graphs) cudaGraphExecDestroy(kv.second);
+        s->pp_graphs.clear();
+        if (s->mb_next) cudaIpcCloseMemHandle(s->mb_next);
+        if (s->mb_prev && s->mb_prev != s->mb_next) cudaIpcCloseMemHandle(s->mb_prev);
+        s->mb_next = s->mb_prev = nullptr; s->mb_on = false;
     }
     return 0;
 }

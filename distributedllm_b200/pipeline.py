@@ -76,3 +76,58 @@ class PipelineStage:
         if r == 0 and w > 1:
             return self.tr.recv((n_tokens, self.n_embd), w - 1) if ring else None
         return y if r == w - 1 else None
+
+
+def join_pipeline(sl, rank: int, world: int, broadcast_bytes: Callable[[Optional[bytes], int], bytes],
+                  all_gather_bytes: Callable[[bytes], Sequence[bytes]], peer: bool = True) -> str:
+    """Bring one rank's slice (`capi.Slice`) into the layer-slice pipeline of `world` ranks and pick the hand-off
+    transport.  The host only moves a few bytes of set-up data through the two collectives it is given
+    (`torch.distributed` in bench.py / the tests; anything else works):
+
+      1. rank 0 draws the ncclUniqueId, everyone joins the communicator (`b200_pipeline_init`) -- the single
+         ncclSend/ncclRecv hop stays available as the tested fallback;
+      2. every rank exports the cudaIpc handle of its mailbox, the handles are all-gathered, every rank maps its ring
+         neighbours (`b200_pipeline_mailbox_connect`): from then on the hop is a peer-memory store + flag inside the
+         step's CUDA graph;
+      3. the ranks agree: if ANY rank could not map a neighbour (no P2P / IPC in this container), all stay on NCCL.
+    Returns "peer" or "nccl"."""
+    from . import capi
+    lib = capi.lib()
+    raw = np.zeros(128, np.uint8)
+    if rank == 0:
+        capi.check(lib.b200_pipeline_unique_id(raw.ctypes.data))
+    raw = np.frombuffer(broadcast_bytes(raw.tobytes() if rank == 0 else None, 128), np.uint8).copy()
+    capi.check(lib.b200_pipeline_init(sl.handle, rank, world, raw.ctypes.data))
+    if not peer or world < 2:
+        return "nccl"
+    h = np.zeros(64, np.uint8)
+    ok = lib.b200_pipeline_mailbox_export(sl.handle, h.ctypes.data) == 0
+    handles = list(all_gather_bytes(h.tobytes() + bytes([1 if ok else 0])))
+    ok = all(x[64] == 1 for x in handles)
+    if ok:
+        buf = np.frombuffer(b"".join(x[:64] for x in handles), np.uint8).copy()
+        ok = lib.b200_pipeline_mailbox_connect(sl.handle, buf.ctypes.data, world) == 0
+        ok = ok and lib.b200_pipeline_transport(sl.handle) == 1
+    agreed = all(x == b"\x01" for x in all_gather_bytes(b"\x01" if ok else b"\x00"))
+    capi.check(lib.b200_pipeline_set_transport(sl.handle, 1 if agreed else 0))
+    return "peer" if agreed else "nccl"
+
+
+def torch_collectives(dist, device):
+    """(broadcast_bytes, all_gather_bytes) over an initialised torch.distributed group (any backend)."""
+    import torch
+
+    def broadcast_bytes(data: Optional[bytes], n: int) -> bytes:
+        t = torch.zeros(n, dtype=torch.uint8, device=device)
+        if data is not None:
+            t.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def all_gather_bytes(data: bytes):
+        mine = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(device)
+        outs = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(outs, mine)
+        return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+    return broadcast_bytes, all_gather_bytes

@@ -165,6 +165,18 @@ int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int r
  * between the slices).  Every rank passes the same session list. */
 int b200_pipeline_step_session(b200_slice_t * s, int session, const float * d_in, int n_tokens, int ring);
 int b200_pipeline_step_batch(b200_slice_t * s, const int * sessions, int n_seq, const float * d_in, int ring);
+/* Peer-memory hand-off (the B200-native hop): every rank owns a MAILBOX in its HBM (sequence flags + two inbox slots of
+ * [n_ctx][n_embd] f32) that its ring neighbours map over NVLink with cudaIpc.  After b200_pipeline_init, each rank
+ * exports its 64-byte handle, the host gathers all of them (torch.distributed all_gather, a file, ...) and every rank
+ * connects.  From then on b200_pipeline_step* hands the activation over with a store into the next rank's mailbox + a
+ * flag, written by the slice's last kernel and polled by the next slice's first kernel inside the captured step graph:
+ * no host code, no NCCL kernel between slices.  B200_PP_PEER=0 (or never connecting) keeps ncclSend / ncclRecv. */
+int b200_pipeline_mailbox_export(b200_slice_t * s, void * handle64);
+int b200_pipeline_mailbox_connect(b200_slice_t * s, const void * handles /* nranks x 64 bytes, rank order */, int nranks);
+int b200_pipeline_transport(b200_slice_t * s);   /* 1 = peer mailboxes, 0 = NCCL */
+int b200_pipeline_set_transport(b200_slice_t * s, int peer);   /* all ranks alike; 1 only after a successful connect */
+int b200_pipeline_error(b200_slice_t * s);       /* non-zero: a mailbox poll timed out (8 s) on this rank */
+
 /* Device pointer of the pipeline's final activation: on rank 0 after a ring step the last slice's output, else dev_out. */
 float * b200_pipeline_result(b200_slice_t * s);
 int b200_pipeline_destroy(b200_slice_t * s);

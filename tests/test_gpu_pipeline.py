@@ -1,4 +1,5 @@
-"""GPU, 2 ranks: the NCCL layer-slice pipeline (b200_pipeline_*) against the un-sliced model on one GPU."""
+"""GPU, 2 ranks: the layer-slice pipeline (b200_pipeline_*) against the un-sliced model on one GPU, once per hand-off
+transport: the peer-memory mailboxes (store + flag over NVLink inside the step graph) and the single ncclSend/ncclRecv."""
 import os
 import subprocess
 import sys
@@ -25,12 +26,10 @@ if not os.path.exists(p):
     ggjt.write_synth_slice(p, sh, a, b, ggjt.T_Q4_0, seed=0)
 sl = capi.Slice(p, local, 64, n_sessions=4)
 lib = capi.lib()
-idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-if rank == 0:
-    raw = np.zeros(128, np.uint8); capi.check(lib.b200_pipeline_unique_id(raw.ctypes.data)); idbuf.copy_(torch.from_numpy(raw))
-dist.broadcast(idbuf, 0)
-raw = idbuf.cpu().numpy().copy()
-capi.check(lib.b200_pipeline_init(sl.handle, rank, world, raw.ctypes.data))
+from distributedllm_b200.pipeline import join_pipeline, torch_collectives
+bcast, gather = torch_collectives(dist, torch.device("cuda", local))
+want_peer = os.environ.get("B200_PP_PEER", "1") != "0"
+transport = join_pipeline(sl, rank, world, bcast, gather, peer=want_peer)
 lib.b200_pipeline_result.restype = C.c_void_p; lib.b200_pipeline_result.argtypes = [C.c_void_p]
 cudart = C.CDLL("libcudart.so.12")
 rng = np.random.default_rng(21)
@@ -73,21 +72,43 @@ for step in range(4):
         got = fetch(3)
         for j, k in enumerate(ids):
             ok = ok and bool((got[j].view(np.uint32) == ref.session_forward(int(k), x[j:j + 1])[0].view(np.uint32)).all())
+# decode steps back to back with no host synchronisation in between (graph replays; the mailbox slots must not be overrun)
+if rank == 0:
+    ref.clear_context()
+sl.clear_context()
+dist.barrier()
+xs = rng.standard_normal((24, sh.n_embd), dtype=np.float32)
+outs = []
+for i in range(24):
+    if rank == 0:
+        assert cudart.cudaMemcpy(C.c_void_p(sl.dev_in), C.c_void_p(xs[i:i + 1].ctypes.data), C.c_size_t(xs[i:i + 1].nbytes), 1) == 0
+    capi.check(lib.b200_pipeline_step(sl.handle, C.c_void_p(sl.dev_in), 1, 1))
+    if rank == 0:
+        sl.sync()
+        outs.append(fetch(1))
+sl.sync()
+if rank == 0:
+    for i in range(24):
+        ok = ok and bool((outs[i].view(np.uint32) == ref.forward(xs[i:i + 1]).view(np.uint32)).all())
 dist.barrier()
 capi.check(lib.b200_pipeline_destroy(sl.handle))
+err = lib.b200_pipeline_error(sl.handle)
 if rank == 0:
-    print("PIPELINE_OK" if ok else "PIPELINE_MISMATCH")
+    print(("PIPELINE_OK" if ok and not err else "PIPELINE_MISMATCH") + " transport=" + transport)
 dist.destroy_process_group()
 '''
 
 
-def test_two_gpu_nccl_pipeline_bit_exact(tmp_path):
+@pytest.mark.parametrize("peer", [1, 0], ids=["peer-mailbox", "nccl"])
+def test_two_gpu_pipeline_bit_exact(tmp_path, peer):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT, "tmp": str(tmp_path)})
+    env = dict(os.environ, B200_PP_PEER=str(peer))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
-                         capture_output=True, text=True, timeout=600)
+                          "--master-addr", "127.0.0.1", "--master-port", str(29533 + peer), str(script)],
+                         capture_output=True, text=True, timeout=600, env=env)
     assert "PIPELINE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+    assert ("transport=peer" if peer else "transport=nccl") in out.stdout, out.stdout[-500:]
