@@ -6,10 +6,13 @@
 // saturated memory system, and the narrow matrices (wo, w2) start cold.  Here ONE kernel runs all layers:
 //
 //   * grid = one CTA per SM, 16 consumer warps (4 GROUPS of 4 warps) + 1 producer warp;
-//   * every group owns a ring of shared-memory stages; lane g of the producer warp streams the weight tiles of group g
-//     in schedule order -- qkv, wo, w1|w3, w2 of layer 0, then layer 1, ... -- with 1-D TMA bulk copies.  The producer
-//     never waits for an activation: weights do not depend on them, so the HBM stream runs THROUGH every dependency of
-//     the layer (RMSNorm, attention, SiLU gate) and is only ever throttled by ring space;
+//   * the CTA owns ONE ring of shared-memory stages (all the shared memory that is left, ~184 KB) fed by one producer
+//     lane in a fixed global order: layer by layer, matrix by matrix (qkv, wo, w1|w3, w2), and inside a matrix the
+//     stages of the CTA's active groups interleaved round-robin.  Whatever is being consumed therefore has the WHOLE
+//     ring in flight -- one group on a narrow matrix (wo, w2) as much as three groups on a wide one -- and the ring
+//     runs ahead into the next matrix / layer while the consumers sit in a dependency.  The producer never waits for
+//     an activation (weights do not depend on them): the HBM stream runs THROUGH every dependency of the layer
+//     (RMSNorm, attention, SiLU gate) and is only ever throttled by ring space;
 //   * consumers walk the same schedule.  Phases are separated by grid-wide progress counters in global memory
 //     (release: fence + atomicAdd by the group that finished its tiles; acquire: one polling thread per CTA + CTA
 //     barrier), not by kernel boundaries;
@@ -55,7 +58,7 @@ struct PersistArgs {
     const float2 * cs; const uint16_t * texp, * tsilu;
     int * cnt;                             // [L][kPPhases], zero before the launch
     float kq_scale;
-    int NS;                                // ring stages per group
+    int NS;                                // ring slots of the CTA
     unsigned long long * trace;            // optional [cta][L][kPTraceSlots]
 };
 
@@ -66,7 +69,7 @@ struct PSmem {
 __host__ __device__ inline PSmem p_smem_layout(int wt, int NS, int nbq_max, int E, int n_ctx) {
     PSmem m;
     size_t off = 0;
-    m.ring = off;    off += (size_t) kPGroups * NS * p_slot_bytes(wt);
+    m.ring = off;    off += (size_t) NS * p_slot_bytes(wt);
     m.a_s = off;     off += (size_t) nbq_max * 128;
     m.da_s = off;    off += (size_t) nbq_max * 16;
     // attention scratch: scores f32 [n_ctx] | p16 [n_ctx] | partials [4][8][128] f32 | q,k,v rows fp16
@@ -76,7 +79,7 @@ __host__ __device__ inline PSmem p_smem_layout(int wt, int NS, int nbq_max, int 
     m.gq = off;      off += (size_t) kPGroups * 32 * 4;
     m.red = off;     off += 16 * 8 + 16 * 4 + 64;
     off = (off + 7) & ~(size_t) 7;
-    m.bars = off;    off += (size_t) 2 * kPGroups * NS * 8;
+    m.bars = off;    off += (size_t) 2 * NS * 8;
     m.total = off;
     return m;
 }
@@ -84,34 +87,59 @@ __host__ __device__ inline PSmem p_smem_layout(int wt, int NS, int nbq_max, int 
 __device__ __forceinline__ int ld_acquire_gpu(const int * p) {
     int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
+__device__ __forceinline__ int ld_relaxed_gpu(const int * p) {
+    int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+// release-add: the group's result stores (made visible to the executing thread by the group barrier before it) are
+// ordered before the counter update at gpu scope -- one instruction instead of membar.gl in every thread + atomicAdd
+__device__ __forceinline__ void red_release_gpu(int * p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
 #define P_TRACE(slot) do { if (a.trace && tid == 0) a.trace[((size_t) blockIdx.x * a.L + il) * kPTraceSlots + (slot)] = gtime(); } while (0)
 
-// ---- per-group ring cursor (identical in every thread of the group, and in the group's producer lane) ---------------
-struct RingCur { int slot, phase; };
+// ---- ring schedule: `idx0` = global stage index at which the current matrix starts; advanced identically by the
+// producer lane and by every consumer thread of the CTA.  Stage `st` of the j-th active group of a round sits at global
+// index idx0 + st * n_act + j, in slot (index % NS), at the slot's (index / NS)-th use.
+struct RingCur { int idx0; long long wait_clk; };
+
+// number of groups of this CTA that own a tile of W in round `round` (groups are filled in order: 0, 1, ...)
+__device__ __forceinline__ int p_active_groups(int n_tiles, int cta, int n_cta, int round) {
+    const int left = n_tiles - round * kPGroups * n_cta - cta;          // tiles of this round at or after this CTA's column
+    if (left <= 0) return 0;
+    const int n = (left + n_cta - 1) / n_cta;
+    return n < kPGroups ? n : kPGroups;
+}
 
 // One weight matrix: the tiles of this group, NC = 1.  EPI_RESID: y[row] = dot + resid[row];  EPI_STORE: y[row] = dot;
 // EPI_GATEQ: g = silu(w1 x) * (w3 x), 32 gate rows of a tile = one Q8_0 block of w2's input, quantised by the group.
-template <int WT, int G, int EPI>
-__device__ __forceinline__ int p_run_matrix(const PersistArgs & a, const PMat & W, RingCur & rc, uint8_t * ring_g, uint64_t * full_g, uint64_t * empty_g,
-                                            const int * a_s, const float * da_s, int gid, int n_groups, int wig, int lane,
+template <int WT, int G, int EPI>            // TR = 4 G row-groups per tile, 4 / G quads per ring stage: one stage = one slot
+__device__ __forceinline__ int p_run_matrix(const PersistArgs & a, const PMat & W, RingCur & rc, uint8_t * ring, uint64_t * full, uint64_t * empty,
+                                            const int * a_s, const float * da_s, int cta, int n_cta, int wig, int lane,
                                             const float * resid, float * y, int out_rows, float * gq_g, int grp) {
     constexpr int CB = (WT == kWT_Q4_0) ? kQ4Chunk : kQ8Chunk;
     constexpr int SLOT = 16 * CB;
-    const int TR = W.TR, sq = W.sq, NS = a.NS;
+    constexpr int TR = kWPC * G, sq = kQS / G;
+    const int NS = a.NS;
     const int n_stage = W.nbq / sq;
-    const bool active = wig * G < TR;                      // warps of the group that own row-groups of a tile
+    constexpr bool active = true;
     const int r = lane >> 2, w = lane & 3;
     int done = 0;
-    for (int tile = gid; tile < W.n_tiles; tile += n_groups) {
+    for (int round = 0; ; round++) {
+        const int n_act = p_active_groups(W.n_tiles, cta, n_cta, round);
+        if (n_act == 0) break;
+        const int tile = (round * kPGroups + grp) * n_cta + cta;
+        if (grp >= n_act) { rc.idx0 += n_stage * n_act; continue; }
         float acc[G][2];
         #pragma unroll
         for (int g = 0; g < G; g++) { acc[g][0] = 0.f; acc[g][1] = 0.f; }
+        int slot = (rc.idx0 + grp) % NS, use = (rc.idx0 + grp) / NS;
         for (int st = 0; st < n_stage; st++) {
-            mbar_wait(&full_g[rc.slot], rc.phase);
+            if (a.trace) { const long long c0 = clock64(); mbar_wait(&full[slot], use & 1); rc.wait_clk += clock64() - c0; }
+            else mbar_wait(&full[slot], use & 1);
             if (active) {
-                const uint8_t * base = ring_g + (size_t) rc.slot * SLOT + (size_t)(wig * G) * CB;
-                #pragma unroll 2
+                const uint8_t * base = ring + (size_t) slot * SLOT + (size_t)(wig * G) * CB;
+                #pragma unroll
                 for (int qi = 0; qi < sq; qi++) {
                     const int Q = st * sq + qi;
                     uint4 wv[G], wv2[G]; uint2 sc[G];
@@ -149,9 +177,10 @@ __device__ __forceinline__ int p_run_matrix(const PersistArgs & a, const PMat & 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_g[rc.slot]);
-            if (++rc.slot == NS) { rc.slot = 0; rc.phase ^= 1; }
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            slot += n_act; if (slot >= NS) { slot -= NS; use++; }
         }
+        rc.idx0 += n_stage * n_act;
         // hsum_float_8 order ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7))
         float res[G];
         #pragma unroll
@@ -184,41 +213,67 @@ __device__ __forceinline__ int p_run_matrix(const PersistArgs & a, const PMat & 
     return done;
 }
 
-// RMSNorm * weight -> Q8_0 act-quant of the row x[K] into a_s / da_s (the fused prologue of k_gemv, 512 threads).
+// RMSNorm * weight -> Q8_0 act-quant of the row x[K] into a_s / da_s: the arithmetic of k_gemv's fused prologue, spread
+// over all 512 consumer threads -- FOUR threads per 32-value block (8 values each: coalesced 32-byte loads, the block's
+// amax by two shuffles, two packed words per thread), up to two blocks per thread-quad (K <= 8192).
 template <int WT>
 __device__ __forceinline__ void p_pro_norm_quant(const float * x, const float * nw, int K, int nb, int nbq, int * a_s, float * da_s,
                                                  double * red, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
-    const bool own = tid < nb;
-    float v[32], wn[32];
+    const int warp = tid >> 5, lane = tid & 31, j = tid & 3;
+    float v[2][8], wn[2][8];
     #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const float4 t = own ? __ldcg((const float4 *)(x + tid * 32 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 u = own ? ldg_keep(nw + tid * 32 + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
-        wn[j*4] = u.x; wn[j*4+1] = u.y; wn[j*4+2] = u.z; wn[j*4+3] = u.w;
+    for (int it = 0; it < 2; it++) {
+        const int b = (tid >> 2) + 128 * it;
+        const bool own = b < nb;
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float4 t = own ? __ldcg((const float4 *)(x + b * 32 + j * 8 + h * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 u = own ? ldg_keep(nw + b * 32 + j * 8 + h * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[it][h*4] = t.x; v[it][h*4+1] = t.y; v[it][h*4+2] = t.z; v[it][h*4+3] = t.w;
+            wn[it][h*4] = u.x; wn[it][h*4+1] = u.y; wn[it][h*4+2] = u.z; wn[it][h*4+3] = u.w;
+        }
     }
     for (int b = nb + tid; b < nbq * 4; b += kPConsumers) {            // padding blocks
         int * dst = a_s + (b >> 2) * 32 + (b & 3) * 2;
         for (int w = 0; w < 4; w++) { dst[w * 8] = 0; dst[w * 8 + 1] = 0; }
         da_s[b] = 0.f;
     }
-    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    double s = 0.0;
     #pragma unroll
-    for (int j = 0; j < 32; j++) s4[j & 3] += widen_nonneg(fmul(v[j], v[j]));
-    double s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    for (int it = 0; it < 2; it++)
+        #pragma unroll
+        for (int e = 0; e < 8; e++) s += widen_nonneg(fmul(v[it][e], v[it][e]));
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) red[warp] = s;
     named_bar_sync(1, kPConsumers);
-    const int nw_used = (nb + 31) >> 5;
-    double tot;
-    if (nw_used == 4) tot = (red[0] + red[1]) + (red[2] + red[3]);       // the order of k_gemv's fused prologue
-    else { tot = 0.0; for (int i = 0; i < nw_used; i++) tot += red[i]; }
+    double tot = 0.0;
+    #pragma unroll
+    for (int i = 0; i < 16; i++) tot += red[i];
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) K), 1e-6f)));
-    if (own) {
+    #pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int b = (tid >> 2) + 128 * it;
+        const bool own = b < nb;
+        float q[8];
+        float amax = 0.f;
         #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = fmul(fmul(v[j], scale), wn[j]);
-        thread_quant_block<WT>(v, a_s, da_s, tid);
+        for (int e = 0; e < 8; e++) { q[e] = fmul(fmul(v[it][e], scale), wn[it][e]); amax = fmaxf(amax, fabsf(q[e])); }
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        if (own) {
+            const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
+            const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
+            int * dst = a_s + (b >> 2) * 32 + (b & 3) * 2;
+            #pragma unroll
+            for (int k = 0; k < 2; k++) {
+                uint32_t pk = 0;
+                #pragma unroll
+                for (int e = 0; e < 4; e++) pk |= ((uint32_t)(rint_small(fmul(q[k*4 + e], id)) & 0xFF)) << (8 * e);
+                const int ww = 2 * j + k;                          // 32-bit word of the block: values 4 ww .. 4 ww + 3
+                dst[(ww & 3) * 8 + (ww >> 2)] = (int) pk;
+            }
+            if (j == 0) da_s[b] = (WT == kWT_Q4_0) ? fmul(d, 0.0625f) : d;
+        }
     }
     named_bar_sync(1, kPConsumers);
 }
@@ -234,7 +289,7 @@ __device__ __forceinline__ void p_pro_preq(const int * aq, const float * da, int
 
 // grid-wide dependency: one thread polls the progress counter, the CTA barrier releases everybody
 __device__ __forceinline__ void p_wait_counter(const int * cnt, int target, int tid) {
-    if (tid == 0) { while (ld_acquire_gpu(cnt) < target) { } }
+    if (tid == 0) { while (ld_relaxed_gpu(cnt) < target) { } (void) ld_acquire_gpu(cnt); }
     named_bar_sync(1, kPConsumers);
 }
 
@@ -274,39 +329,46 @@ __device__ __forceinline__ void p_attention_head(const PersistArgs & a, const PL
         for (int c = 0; c < 4; c++)
             #pragma unroll
             for (int e = 0; e < 8; e++) qf[c][e] = h2f(q16s[32 * c + 8 * ql + e]);
-        for (int t0 = 0; t0 < tcount; t0 += kPConsumers / 4) {
-            const int t = t0 + (tid >> 2);
-            const bool valid = t < tcount;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                uint4 kv[4];
-                if (t == pos) {
-                    #pragma unroll
-                    for (int c = 0; c < 4; c++) kv[c] = *(const uint4 *)(k16s + 32 * c + 8 * ql);
-                } else {
+        // two positions per thread per iteration: 8 x 16-byte loads in flight hide the (L2 / HBM) latency of the key rows
+        for (int t0 = 0; t0 < tcount; t0 += kPConsumers / 2) {
+            uint4 kv[2][4];
+            bool valid[2];
+            #pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int t = t0 + u * (kPConsumers / 4) + (tid >> 2);
+                valid[u] = t < tcount;
+                if (valid[u] && t != pos) {
                     const uint16_t * krow = kc + (size_t) t * E + h * 128;
                     #pragma unroll
-                    for (int c = 0; c < 4; c++) kv[c] = __ldcg((const uint4 *)(krow + 32 * c + 8 * ql));
+                    for (int c = 0; c < 4; c++) kv[u][c] = __ldcg((const uint4 *)(krow + 32 * c + 8 * ql));
+                } else {
+                    #pragma unroll
+                    for (int c = 0; c < 4; c++) kv[u][c] = *(const uint4 *)(k16s + 32 * c + 8 * ql);
                 }
+            }
+            #pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int t = t0 + u * (kPConsumers / 4) + (tid >> 2);
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    const uint32_t u[4] = {kv[c].x, kv[c].y, kv[c].z, kv[c].w};
+                    const uint32_t w4[4] = {kv[u][c].x, kv[u][c].y, kv[u][c].z, kv[u][c].w};
                     #pragma unroll
                     for (int e = 0; e < 8; e++) {
-                        const uint16_t kh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
+                        const uint16_t kh = (uint16_t)(w4[e >> 1] >> (16 * (e & 1)));
                         acc[e] = ffma(h2f(kh), qf[c][e], acc[e]);
                     }
                 }
+                float v8[8];
+                #pragma unroll
+                for (int e = 0; e < 8; e++) {                        // (x0 + x2) + (x1 + x3)
+                    float x = fadd(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], 2));
+                    v8[e] = fadd(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                }
+                const float u0 = fadd(v8[0], v8[4]), u1 = fadd(v8[1], v8[5]), u2 = fadd(v8[2], v8[6]), u3 = fadd(v8[3], v8[7]);
+                const float dot = fadd(fadd(u0, u1), fadd(u2, u3));
+                if (valid[u] && ql == 0) sc[t] = fmul(dot, a.kq_scale);
             }
-            float v8[8];
-            #pragma unroll
-            for (int e = 0; e < 8; e++) {                            // (x0 + x2) + (x1 + x3)
-                float x = fadd(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], 2));
-                v8[e] = fadd(x, __shfl_xor_sync(0xffffffffu, x, 1));
-            }
-            const float u0 = fadd(v8[0], v8[4]), u1 = fadd(v8[1], v8[5]), u2 = fadd(v8[2], v8[6]), u3 = fadd(v8[3], v8[7]);
-            const float dot = fadd(fadd(u0, u1), fadd(u2, u3));
-            if (valid && ql == 0) sc[t] = fmul(dot, a.kq_scale);
         }
     }
     named_bar_sync(1, kPConsumers);
@@ -338,16 +400,27 @@ __device__ __forceinline__ void p_attention_head(const PersistArgs & a, const PL
     {
         const int g = tid >> 7, l = (tid >> 4) & 7, cg = tid & 15;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int t = 8 * g + l; t < lim; t += 32) {
-            uint4 vv;
-            if (t == pos) vv = *(const uint4 *)(v16s + 8 * cg);
-            else vv = __ldcg((const uint4 *)(vc + (size_t) t * E + h * 128 + 8 * cg));
-            const uint32_t u[4] = {vv.x, vv.y, vv.z, vv.w};
-            const float p = h2f(p16[t]);
+        // four value rows in flight per thread; the FMAs stay in position order (slot accumulators of ggml_vec_dot_f16)
+        for (int tb = 8 * g + l; tb < lim; tb += 128) {
+            uint4 vv[4];
             #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const uint16_t vh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
-                acc[e] = ffma(h2f(vh), p, acc[e]);
+            for (int u = 0; u < 4; u++) {
+                const int t = tb + 32 * u;
+                if (t < lim && t != pos) vv[u] = __ldcg((const uint4 *)(vc + (size_t) t * E + h * 128 + 8 * cg));
+                else vv[u] = *(const uint4 *)(v16s + 8 * cg);
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int t = tb + 32 * u;
+                if (t < lim) {
+                    const uint32_t w4[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+                    const float p = h2f(p16[t]);
+                    #pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const uint16_t vh = (uint16_t)(w4[e >> 1] >> (16 * (e & 1)));
+                        acc[e] = ffma(h2f(vh), p, acc[e]);
+                    }
+                }
             }
         }
         float4 * dst = (float4 *)(partl + (g * 8 + l) * 128 + 8 * cg);
@@ -393,24 +466,20 @@ __global__ void __launch_bounds__(kPThreads, 1) k_decode_persistent(const Persis
     double * redd = (double *)(smem + lay.red);
     float * redf = (float *)(redd + 16);
     uint64_t * full = (uint64_t *)(smem + lay.bars);
-    uint64_t * empty = full + kPGroups * a.NS;
+    uint64_t * empty = full + a.NS;
 
     const int tid = threadIdx.x, NS = a.NS;
-    const int cta = blockIdx.x, n_cta = gridDim.x, n_groups = kPGroups * n_cta;
+    const int cta = blockIdx.x, n_cta = gridDim.x;
     if (tid == 0) {
-        for (int i = 0; i < kPGroups * NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], kWPC); }
+        for (int i = 0; i < NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], kWPC); }
         mbar_fence_init();
     }
     __syncthreads();
 
     if (tid >= kPConsumers) {
-        // ------------------------------------------------------------------ producer warp: lane g feeds group g
-        const int g = tid - kPConsumers;
-        if (g < kPGroups) {
-            const int gid = g * n_cta + cta;
-            uint8_t * ring_g = ring + (size_t) g * NS * SLOT;
-            uint64_t * full_g = full + g * NS, * empty_g = empty + g * NS;
-            int slot = 0, use = 0;
+        // ------------------------------------------------------------------ producer: one lane feeds the CTA's ring
+        if (tid == kPConsumers) {
+            int idx = 0;
             for (int il = 0; il < a.L; il++) {
                 const PLayer & Lw = a.layers[il];
                 #pragma unroll 1
@@ -418,13 +487,18 @@ __global__ void __launch_bounds__(kPThreads, 1) k_decode_persistent(const Persis
                     const PMat & W = ph == 0 ? Lw.qkv : (ph == 1 ? Lw.wo : (ph == 2 ? Lw.w13 : Lw.w2));
                     const int n_stage = W.nbq / W.sq;
                     const uint32_t bytes = (uint32_t)(W.sq * W.TR * CB);
-                    for (int tile = gid; tile < W.n_tiles; tile += n_groups) {
-                        const uint8_t * src = W.data + (long long) tile * W.tile_bytes;
+                    for (int round = 0; ; round++) {
+                        const int n_act = p_active_groups(W.n_tiles, cta, n_cta, round);
+                        if (n_act == 0) break;
+                        const uint8_t * src0 = W.data + (long long)(round * kPGroups * n_cta + cta) * W.tile_bytes;
+                        const long long gstride = (long long) n_cta * W.tile_bytes;      // next group's tile
                         for (int st = 0; st < n_stage; st++) {
-                            if (use > 0) mbar_wait(&empty_g[slot], (use - 1) & 1);
-                            mbar_arrive_expect_tx(&full_g[slot], bytes);
-                            bulk_g2s(ring_g + (size_t) slot * SLOT, src + (size_t) st * bytes, bytes, &full_g[slot]);
-                            if (++slot == NS) { slot = 0; use++; }
+                            for (int j = 0; j < n_act; j++, idx++) {
+                                const int slot = idx % NS, use = idx / NS;
+                                if (use > 0) { while (!mbar_try_wait(&empty[slot], (use - 1) & 1)) __nanosleep(64); }
+                                mbar_arrive_expect_tx(&full[slot], bytes);
+                                bulk_g2s(ring + (size_t) slot * SLOT, src0 + j * gstride + (size_t) st * bytes, bytes, &full[slot]);
+                            }
                         }
                     }
                 }
@@ -435,9 +509,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_decode_persistent(const Persis
 
     // ---------------------------------------------------------------------- consumers
     const int grp = tid >> 7, wig = (tid >> 5) & 3, lane = tid & 31;
-    const int gid = grp * n_cta + cta;
-    uint8_t * ring_g = ring + (size_t) grp * NS * SLOT;
-    uint64_t * full_g = full + grp * NS, * empty_g = empty + grp * NS;
     float * gq_g = gq + grp * 32;
     RingCur rc{0, 0};
     const int pos = *a.n_past;
@@ -453,19 +524,18 @@ __global__ void __launch_bounds__(kPThreads, 1) k_decode_persistent(const Persis
             P_TRACE(0);
             p_pro_norm_quant<WT>(Lw.x_in, Lw.attn_norm, K_E, a.nb_E, a.nbqE, a_s, da_s, redd, tid);
             P_TRACE(1);
-            const int done = p_run_matrix<WT, 1, EPI_STORE>(a, Lw.qkv, rc, ring_g, full_g, empty_g, a_s, da_s, gid, n_groups, wig, lane,
+            const int done = p_run_matrix<WT, 1, EPI_STORE>(a, Lw.qkv, rc, ring, full, empty, a_s, da_s, cta, n_cta, wig, lane,
                                                             nullptr, a.qkv, 3 * a.E, gq_g, grp);
-            if (done) { __threadfence(); named_bar_sync(2 + grp, kConsumers); if ((tid & 127) == 0) atomicAdd(cnt + 0, done); }
             P_TRACE(2);
+            if (done) { named_bar_sync(2 + grp, kConsumers); if ((tid & 127) == 0) red_release_gpu(cnt + 0, done); }
         }
         // ---- attention, one head per CTA
         if (cta < a.H) {
             p_wait_counter(cnt + 0, Lw.qkv.n_tiles, tid);
             P_TRACE(3);
             p_attention_head(a, Lw, cta, pos, scratch, redf, redd, tid);
-            __threadfence();
             named_bar_sync(1, kPConsumers);
-            if (tid == 0) atomicAdd(cnt + 1, 1);
+            if (tid == 0) red_release_gpu(cnt + 1, 1);
             P_TRACE(4);
         }
         // ---- ffin = Wo . att + x
@@ -473,32 +543,36 @@ __global__ void __launch_bounds__(kPThreads, 1) k_decode_persistent(const Persis
             p_wait_counter(cnt + 1, a.H, tid);
             P_TRACE(5);
             p_pro_preq(a.aq_att, a.da_att, a.nbqE, a_s, da_s, tid);
-            const int done = p_run_matrix<WT, 1, EPI_RESID>(a, Lw.wo, rc, ring_g, full_g, empty_g, a_s, da_s, gid, n_groups, wig, lane,
-                                                            Lw.x_in, a.ffin, a.E, gq_g, grp);
-            if (done) { __threadfence(); named_bar_sync(2 + grp, kConsumers); if ((tid & 127) == 0) atomicAdd(cnt + 2, done); }
             P_TRACE(6);
+            const int done = p_run_matrix<WT, 1, EPI_RESID>(a, Lw.wo, rc, ring, full, empty, a_s, da_s, cta, n_cta, wig, lane,
+                                                            Lw.x_in, a.ffin, a.E, gq_g, grp);
+            P_TRACE(7);
+            if (done) { named_bar_sync(2 + grp, kConsumers); if ((tid & 127) == 0) red_release_gpu(cnt + 2, done); }
         }
         // ---- gate = silu(W1 . n) * (W3 . n),  n = q8(rmsnorm(ffin) * w)
         if (cta < Lw.w13.n_tiles) {
             p_wait_counter(cnt + 2, Lw.wo.n_tiles, tid);
-            P_TRACE(7);
-            p_pro_norm_quant<WT>(a.ffin, Lw.ffn_norm, K_E, a.nb_E, a.nbqE, a_s, da_s, redd, tid);
             P_TRACE(8);
-            const int done = p_run_matrix<WT, 2, EPI_GATEQ>(a, Lw.w13, rc, ring_g, full_g, empty_g, a_s, da_s, gid, n_groups, wig, lane,
-                                                            nullptr, nullptr, K_F, gq_g, grp);
-            if (done) { __threadfence(); named_bar_sync(2 + grp, kConsumers); if ((tid & 127) == 0) atomicAdd(cnt + 3, done); }
+            p_pro_norm_quant<WT>(a.ffin, Lw.ffn_norm, K_E, a.nb_E, a.nbqE, a_s, da_s, redd, tid);
             P_TRACE(9);
+            const int done = p_run_matrix<WT, 2, EPI_GATEQ>(a, Lw.w13, rc, ring, full, empty, a_s, da_s, cta, n_cta, wig, lane,
+                                                            nullptr, nullptr, K_F, gq_g, grp);
+            P_TRACE(10);
+            if (done) { named_bar_sync(2 + grp, kConsumers); if ((tid & 127) == 0) red_release_gpu(cnt + 3, done); }
         }
         // ---- x_out = W2 . gate + ffin
         if (cta < Lw.w2.n_tiles) {
             p_wait_counter(cnt + 3, Lw.w13.n_tiles, tid);
-            P_TRACE(10);
-            p_pro_preq(a.aq_gate, a.da_gate, a.nbqF, a_s, da_s, tid);
-            const int done = p_run_matrix<WT, 1, EPI_RESID>(a, Lw.w2, rc, ring_g, full_g, empty_g, a_s, da_s, gid, n_groups, wig, lane,
-                                                            a.ffin, Lw.x_out, a.E, gq_g, grp);
-            if (done) { __threadfence(); named_bar_sync(2 + grp, kConsumers); if ((tid & 127) == 0) atomicAdd(cnt + 4, done); }
             P_TRACE(11);
+            p_pro_preq(a.aq_gate, a.da_gate, a.nbqF, a_s, da_s, tid);
+            P_TRACE(12);
+            const int done = p_run_matrix<WT, 1, EPI_RESID>(a, Lw.w2, rc, ring, full, empty, a_s, da_s, cta, n_cta, wig, lane,
+                                                            a.ffin, Lw.x_out, a.E, gq_g, grp);
+            P_TRACE(13);
+            if (done) { named_bar_sync(2 + grp, kConsumers); if ((tid & 127) == 0) red_release_gpu(cnt + 4, done); }
+            P_TRACE(14);
         }
+        if (a.trace && tid == 0) { a.trace[((size_t) blockIdx.x * a.L + il) * kPTraceSlots + 15] = (unsigned long long) rc.wait_clk; rc.wait_clk = 0; }
     }
 }
 

@@ -260,9 +260,7 @@ static bool persist_applicable(const b200_slice * s, int N) {
 static PMat pmat_of(const PackedW & W, int G) {
     PMat m{};
     m.data = W.data; m.n_tiles = W.n_tiles; m.nbq = W.nbq; m.TR = W.TR; m.tile_bytes = W.tile_bytes;
-    int sq = 16 / W.TR;                       // quads per stage: sq * TR * chunk <= slot (16 chunks)
-    while (sq > 1 && W.nbq % sq) sq >>= 1;
-    m.sq = sq; (void) G;
+    m.sq = kQS / G;                           // quads per ring stage: one stage = 16 chunks = one slot
     return m;
 }
 
@@ -279,9 +277,9 @@ static int persist_prepare(b200_slice * s, const float * in, float * out) {
         LayerW & Lw = s->layers[il];
         PLayer & P = tab[il];
         P.qkv = pmat_of(Lw.qkv, 1);
-        P.wo = pmat_of(Lw.wo_p.data ? Lw.wo_p : Lw.wo, 1);
+        P.wo = pmat_of(Lw.wo, 1);
         P.w13 = pmat_of(Lw.w13, 2);
-        P.w2 = pmat_of(Lw.w2_p.data ? Lw.w2_p : Lw.w2, 1);
+        P.w2 = pmat_of(Lw.w2, 1);
         P.attn_norm = Lw.attn_norm; P.ffn_norm = Lw.ffn_norm;
         float * nxt = (il == s->L - 1) ? out : ((il & 1) ? s->xb : s->xa);
         P.x_in = cur; P.x_out = nxt;
@@ -312,8 +310,8 @@ static int launch_persistent(b200_slice * s, const float * in, float * out) {
     a.trace = s->p_trace;
     const int nbq_max = s->nbqF > s->nbqE ? s->nbqF : s->nbqE;
     const size_t limit = 227 * 1024;
-    int NS = s->persist_ns > 0 ? s->persist_ns : 8;
-    while (NS > 2 && p_smem_layout(s->wtype, NS, nbq_max, s->E, s->n_ctx).total > limit) NS--;
+    int NS = s->persist_ns > 0 ? s->persist_ns : 48;          // ring slots of the CTA: all the shared memory that is left
+    while (NS > 4 && p_smem_layout(s->wtype, NS, nbq_max, s->E, s->n_ctx).total > limit) NS--;
     const PSmem lay = p_smem_layout(s->wtype, NS, nbq_max, s->E, s->n_ctx);
     if (lay.total > limit) return fail(B200_EINVAL, "persistent step needs %zu B of shared memory", lay.total);
     a.NS = NS;
@@ -883,11 +881,9 @@ static int load_locked(b200_slice * s, const char * path) {
             } else {
                 LoadJob a; a.nsrc = 3; a.src[0] = &wq; a.src[1] = &wk; a.src[2] = &wv; a.mode = 1; a.G = 1; a.out = &Lw.qkv; jobs.push_back(a);
                 LoadJob o; o.nsrc = 1; o.src[0] = &wo; o.mode = 0; o.G = 1; o.out = &Lw.wo;
-                if (s->use_persist && s->persist_tr != 4) { o.out2 = &Lw.wo_p; o.TR2 = s->persist_tr; }
                 jobs.push_back(o);
                 LoadJob g; g.nsrc = 2; g.src[0] = &w1; g.src[1] = &w3; g.mode = 2; g.G = 2; g.out = &Lw.w13; jobs.push_back(g);
                 LoadJob d; d.nsrc = 1; d.src[0] = &w2; d.mode = 0; d.G = 1; d.out = &Lw.w2;
-                if (s->use_persist && s->persist_tr != 4) { d.out2 = &Lw.w2_p; d.TR2 = s->persist_tr; }
                 jobs.push_back(d);
             }
             s->weight_bytes += (int64_t)(an.nbytes + fn.nbytes + wq.nbytes + wk.nbytes + wv.nbytes + wo.nbytes + w1.nbytes + w2.nbytes + w3.nbytes);
@@ -1003,12 +999,29 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->use_persist = env_int("B200_PERSIST", 0) != 0;         // single-token step as ONE persistent kernel (persist.cuh)
     s->persist_tr = env_int("B200_PERSIST_TR", 4); s->persist_ns = env_int("B200_PERSIST_NS", 0); s->persist_ctas = env_int("B200_PERSIST_CTAS", 0);
     if (s->persist_tr != 1 && s->persist_tr != 2 && s->persist_tr != 4) s->persist_tr = 4;
+    const bool want_ptrace = env_int("B200_PTRACE", 0) != 0;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
     int rc = load_locked(s, path);
     if (rc) { destroy(s); return rc; }
+    if (want_ptrace) {
+        const size_t n = (size_t) s->n_sm * s->L * kPTraceSlots;
+        if ((rc = dev_alloc(s, &s->p_trace, n))) { destroy(s); return rc; }
+        cudaMemset(s->p_trace, 0, n * 8);
+    }
     *out = s;
     return 0;
+}
+
+/* Debug timeline of the persistent step (B200_PTRACE=1 at load): [cta][layer][16] %globaltimer stamps of the LAST step. */
+int b200_debug_ptrace_read(b200_slice_t * s, unsigned long long * out, size_t cap_words) {
+    if (!s || !s->p_trace || !out) return 0;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    size_t n = (size_t) s->n_sm * s->L * kPTraceSlots;
+    if (n > cap_words) n = cap_words;
+    cudaMemcpy(out, s->p_trace, n * 8, cudaMemcpyDeviceToHost);
+    return (int)(n / kPTraceSlots);
 }
 
 int b200_slice_unload(b200_slice_t * s) {
