@@ -130,8 +130,60 @@ __global__ void k_repack(RepackArgs a) {
 //     shared memory in dp4a word order
 //   * epilogue (fused): store | + residual | SiLU(w1 x) * (w3 x)
 // =============================================================================================
+// =============================================================================================
+// Inter-slice hand-off through PEER MEMORY (NVLink / NVSwitch), no host and no NCCL kernel in the path.
+// Every rank owns a MAILBOX in its own HBM, mapped into its ring neighbours (cudaIpc):
+//     ack                    written by the NEXT rank: highest sequence number it has consumed from OUR sends
+//     inbox[kMbSlots][n_ctx * n_embd] of 8-byte ELEMENTS {f32 bits, sequence number}
+// The payload carries its own flag ("LL" style: a 64-bit store is single-copy atomic, so a reader that sees the sequence
+// number in the high word has the value in the low word): the sender needs NO fence and NO separate flag write, the
+// latency of a hop is one NVLink store plus a poll.
+//   * sender = the slice's LAST matmul itself for single-token steps (EPI_RESID_SEND: every output row is stored to the
+//     local buffer and, as {value, seq}, into the next rank's inbox the moment it is computed), or k_peer_send for
+//     multi-row steps;
+//   * receiver = k_peer_recv, first kernel of the next slice's step: every thread polls ITS elements until they carry
+//     the expected sequence number, compacts them into the slice's input buffer and acknowledges the slot.  It sits
+//     inside the step's captured graph with programmatic dependent launch: while it polls, the slice's first weight
+//     matmul is already resident and streaming weights into shared memory.
+// Sequence counters are per link and live in device memory, so a graph replay needs no host-side argument.  The sender
+// reuses a slot only after the receiver acknowledged message seq - kMbSlots.  A poll that exceeds kMbTimeoutNs sets
+// *err and falls through (the host reports it) instead of hanging the GPU.
+// =============================================================================================
+constexpr int kMbSlots = 2;
+constexpr unsigned long long kMbTimeoutNs = 8000000000ull;
+
+struct MailboxHdr {              // first 256 bytes of a mailbox block
+    int pad0[16];
+    int ack;                     // remote-written (next rank)
+    int pad1[15];
+    int seq_in, seq_out;         // local counters: messages consumed / produced on my inbound / outbound link
+    int err;                     // local: a poll timed out
+    int cnt_send, cnt_recv;      // local: last-CTA election of multi-CTA sends / receives
+    int pad2[27];
+};
+static_assert(sizeof(MailboxHdr) == 256, "mailbox header layout");
+
+__device__ __forceinline__ int ld_relaxed_sys(const int * p) {
+    int v; asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(int * p, int v) {
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2 * p) {
+    uint2 v; asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_ll(uint2 * p, float val, int seq) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(__float_as_uint(val)), "r"((uint32_t) seq) : "memory");
+}
+// wait until the receiver has consumed message seq - kMbSlots (the slot message `seq` is about to overwrite)
+__device__ __forceinline__ void mb_wait_slot_free(MailboxHdr * mine, int seq) {
+    const unsigned long long t0 = gtime();
+    while (ld_relaxed_sys(&mine->ack) < seq - kMbSlots)
+        if (gtime() - t0 > kMbTimeoutNs) { mine->err = 1; break; }
+}
+
 enum { PRO_PLAIN = 0, PRO_NORM = 1, PRO_PREQ = 2 };
-enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GATE = 2, EPI_GATEQ = 3, EPI_RESID_NQ = 4 };
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GATE = 2, EPI_GATEQ = 3, EPI_RESID_NQ = 4, EPI_RESID_SEND = 5 };
 
 struct GemvArgs {
     PackedW W;
@@ -149,6 +201,9 @@ struct GemvArgs {
     unsigned long long * trace;          // debug timeline (B200_TRACE), or null
     int pre_stages;                      // ring stages the producer may request before the prologue loads are issued
     int dbg_nomath;                      // debug: consume ring stages without computing (streaming-rate probe)
+    // pipeline hand-off folded into the slice's first / last matmul (single-token steps; see "PEER MEMORY" above)
+    MailboxHdr * mb_mine;                // EPI_RESID_SEND: this rank's mailbox (ack, seq_out)
+    uint2 * mb_peer_inbox; size_t mb_slot_elems;   // EPI_RESID_SEND: next rank's inbox (mapped peer memory), elements per slot
 };
 
 __host__ __device__ inline size_t act_bytes_per_col(int nbq) { return (size_t) nbq * (128 + 16); }
@@ -396,6 +451,15 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
 
     const int r = lane >> 2, w = lane & 3;
     int slot = 0, phase = 0;
+    uint2 * send_slot = nullptr; int send_seq = 0;
+    if (EPI == EPI_RESID_SEND) {
+        // last matmul of a pipelined slice (N = 1): every output row also goes, as {value, seq}, into the next rank's inbox
+        // slot the moment it is computed -- no fence, no flag, no extra kernel.  seq_out is advanced by k_advance_pp.
+        send_seq = a.mb_mine->seq_out + 1;
+        if (lane == 0) mb_wait_slot_free(a.mb_mine, send_seq);
+        __syncwarp();
+        send_slot = a.mb_peer_inbox + (size_t)(send_seq & (kMbSlots - 1)) * a.mb_slot_elems;
+    }
     for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
         float acc[G][NC][2];
         #pragma unroll
@@ -498,8 +562,9 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                     for (int n = 0; n < NC; n++) {
                         if (n < ncols) {
                             float v = res[g][n];
-                            if (EPI == EPI_RESID || EPI == EPI_RESID_NQ) v = fadd(v, a.resid[(size_t)(col0 + n) * a.ldr + row]);
+                            if (EPI == EPI_RESID || EPI == EPI_RESID_NQ || EPI == EPI_RESID_SEND) v = fadd(v, a.resid[(size_t)(col0 + n) * a.ldr + row]);
                             a.y[(size_t)(col0 + n) * a.ldy + row] = v;
+                            if (EPI == EPI_RESID_SEND) st_ll(send_slot + row, v, send_seq);   // {value, seq} straight into the next rank's inbox (NVLink)
                             if (EPI == EPI_RESID_NQ) gq[n * 32 + warp * 8 + r] = v;
                         }
                     }
@@ -1126,45 +1191,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     if (threadIdx.x == 0) B200_TRACE(a.trace, 3);
 }
 
-// =============================================================================================
-// Inter-slice hand-off through PEER MEMORY (NVLink / NVSwitch), no host and no NCCL kernel in the path.
-// Every rank owns a MAILBOX in its own HBM, mapped into its ring neighbours (cudaIpc):
-//     flag[kMbSlots]  written by the PREVIOUS rank: sequence number of the message sitting in inbox slot (seq & 1)
-//     ack             written by the NEXT rank: highest sequence number it has consumed from OUR sends
-//     inbox[kMbSlots][n_ctx * n_embd] f32
-// k_peer_send (last kernel of a slice's step) waits until its slot at the receiver is free, stores the activation
-// into the receiver's inbox over NVLink, fences at system scope and publishes the sequence number; k_peer_recv (first
-// kernel of the next slice's step) polls its local flag, copies the slot into the slice's input buffer and acknowledges.
-// Both live inside the step's captured graph with programmatic dependent launch: while k_peer_recv polls, the first
-// weight matmul of the slice is already resident and streaming its weights into shared memory.
-// Sequence counters are per link and live in device memory, so a graph replay needs no host-side argument.
-// A poll that exceeds kMbTimeoutNs sets *err and falls through (the host reports it) instead of hanging the GPU.
-// =============================================================================================
-constexpr int kMbSlots = 2;
-constexpr unsigned long long kMbTimeoutNs = 8000000000ull;
-
-struct MailboxHdr {              // first 256 bytes of a mailbox block
-    int flag[kMbSlots];          // remote-written (previous rank)
-    int pad0[14];
-    int ack;                     // remote-written (next rank)
-    int pad1[15];
-    int seq_in, seq_out;         // local counters
-    int err;                     // local: a poll timed out
-    int pad2[29];
-};
-static_assert(sizeof(MailboxHdr) == 256, "mailbox header layout");
-
-__device__ __forceinline__ int ld_acquire_sys(const int * p) {
-    int v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_release_sys(int * p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-
 struct PeerRecvArgs {
     MailboxHdr * mine;           // local mailbox
-    const float * inbox;         // local inbox base
-    size_t slot_floats;
+    const uint2 * inbox;         // local inbox base
+    size_t slot_elems;
     int * peer_ack;              // &previous rank's mailbox->ack (remote)
     float * dst; int count;      // floats to deliver into the slice's input buffer
 };
@@ -1172,63 +1202,58 @@ struct PeerRecvArgs {
 __global__ void __launch_bounds__(1024) k_peer_recv(const PeerRecvArgs a) {
     if (threadIdx.x == 0) grid_dep_launch();          // the slice's first matmul may start streaming its weights now
     grid_dep_wait();                                  // everything before this step on the stream is done (dst is free)
-    __shared__ int s_seq;
-    if (threadIdx.x == 0) {
-        const int s = a.mine->seq_in + 1;
-        const unsigned long long t0 = gtime();
-        while (ld_acquire_sys(&a.mine->flag[s & (kMbSlots - 1)]) != s) {
+    const int s = a.mine->seq_in + 1;
+    const uint2 * src = a.inbox + (size_t)(s & (kMbSlots - 1)) * a.slot_elems;
+    const unsigned long long t0 = gtime();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += gridDim.x * blockDim.x) {
+        uint2 v = ld_ll(src + i);
+        while ((int) v.y != s) {
             if (gtime() - t0 > kMbTimeoutNs) { a.mine->err = 1; break; }
+            v = ld_ll(src + i);
         }
-        s_seq = s;
+        a.dst[i] = __uint_as_float(v.x);
     }
     __syncthreads();
-    const int s = s_seq;
-    const float4 * src = (const float4 *)(a.inbox + (size_t)(s & (kMbSlots - 1)) * a.slot_floats);
-    float4 * dst = (float4 *) a.dst;
-    for (int i = threadIdx.x; i < a.count / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
-    __syncthreads();
     if (threadIdx.x == 0) {
-        a.mine->seq_in = s;
-        __threadfence_system();
-        st_release_sys(a.peer_ack, s);                // the sender may reuse this slot
+        // the LAST CTA to finish has seen every element: count the message, free the slot for the sender
+        if (gridDim.x == 1 || atomicAdd(&a.mine->cnt_recv, 1) == (int) gridDim.x - 1) {
+            a.mine->cnt_recv = 0;
+            a.mine->seq_in = s;
+            st_relaxed_sys(a.peer_ack, s);
+        }
     }
 }
 
 struct PeerSendArgs {
     MailboxHdr * mine;           // local mailbox (ack, seq_out)
-    MailboxHdr * peer;           // next rank's mailbox (remote): flag
-    float * peer_inbox;          // next rank's inbox base (remote)
-    size_t slot_floats;
+    uint2 * peer_inbox;          // next rank's inbox base (remote)
+    size_t slot_elems;
     const float * src; int count;
 };
 
 __global__ void __launch_bounds__(1024) k_peer_send(const PeerSendArgs a) {
     if (threadIdx.x == 0) grid_dep_launch();
     grid_dep_wait();                                  // src is the previous kernel's output
-    __shared__ int s_seq;
-    if (threadIdx.x == 0) {
-        const int s = a.mine->seq_out + 1;
-        const unsigned long long t0 = gtime();
-        while (ld_acquire_sys(&a.mine->ack) < s - kMbSlots) {      // message s - kMbSlots still occupies the slot
-            if (gtime() - t0 > kMbTimeoutNs) { a.mine->err = 1; break; }
-        }
-        s_seq = s;
-    }
+    const int s = a.mine->seq_out + 1;
+    if (threadIdx.x == 0) mb_wait_slot_free(a.mine, s);
     __syncthreads();
-    const int s = s_seq;
-    float4 * dst = (float4 *)(a.peer_inbox + (size_t)(s & (kMbSlots - 1)) * a.slot_floats);
-    const float4 * src = (const float4 *) a.src;
-    for (int i = threadIdx.x; i < a.count / 4; i += blockDim.x) dst[i] = src[i];
-    __threadfence_system();                           // my stores are performed at the peer before the flag can be seen
+    uint2 * dst = a.peer_inbox + (size_t)(s & (kMbSlots - 1)) * a.slot_elems;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += gridDim.x * blockDim.x) st_ll(dst + i, a.src[i], s);
     __syncthreads();
     if (threadIdx.x == 0) {
-        st_release_sys(&a.peer->flag[s & (kMbSlots - 1)], s);
-        a.mine->seq_out = s;
+        // every CTA read seq_out before the last one finishes, so the last one may advance it
+        if (gridDim.x == 1 || atomicAdd(&a.mine->cnt_send, 1) == (int) gridDim.x - 1) { a.mine->cnt_send = 0; a.mine->seq_out = s; }
     }
 }
 
 // position counter kept on the device so a captured graph can be replayed for every token
 __global__ void k_advance(int * n_past, int by) { grid_dep_wait(); if (threadIdx.x == 0) *n_past += by; }
+// the same for a pipelined slice whose LAST matmul stored its rows into the next rank's inbox (EPI_RESID_SEND): the message
+// is complete when that kernel is, count it
+__global__ void k_advance_sent(int * n_past, int by, MailboxHdr * mine) {
+    grid_dep_wait();
+    if (threadIdx.x == 0) { *n_past += by; mine->seq_out = mine->seq_out + 1; }
+}
 // batched step: every listed session moves one position
 __global__ void k_advance_cols(int * n_past, const int2 * cols, int n) { grid_dep_wait(); if ((int) threadIdx.x < n) n_past[cols[threadIdx.x].x] += 1; }
 

@@ -81,7 +81,10 @@ struct b200_slice {
     // peer-memory hand-off (b200_pipeline_mailbox_*): my mailbox, and my ring neighbours' mailboxes mapped over NVLink
     uint8_t * mb_block = nullptr; size_t mb_slot_floats = 0;
     uint8_t * mb_next = nullptr, * mb_prev = nullptr; bool mb_on = false;
-    bool send_pending = false; PeerSendArgs send_args{};      // enqueue_layers launches the send right behind the last matmul
+    bool send_pending = false; PeerSendArgs send_args{}; int send_ctas = 1;      // enqueue_layers launches the send right behind the last matmul
+    // single-token steps fold the send into the slice's last matmul (EPI_RESID_SEND): rows leave for the next rank's inbox
+    // as they are computed, no k_peer_send launch on the critical path
+    bool fold_send = false, use_fold = true;
     std::map<GraphKey, cudaGraphExec_t> pp_graphs;
     // persistent single-token step (persist.cuh)
     bool use_persist = false; int persist_tr = 4, persist_ns = 0, persist_ctas = 0;
@@ -483,6 +486,12 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
                 w.nq_norm_w = s->layers[il + 1].attn_norm; w.nq_counter = s->nq_counter; w.nq_partial = s->nq_partial; w.aq_out = s->aq_x; w.da_out = s->da_x;
                 w.out_nbq = s->nbqE; w.out_dscale = dsc;
                 if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID_NQ>(s, w))) return rc;
+            } else if (s->fold_send && il == s->L - 1) {
+                w.mb_mine = (MailboxHdr *) s->mb_block;
+                w.mb_peer_inbox = (uint2 *)(s->mb_next + sizeof(MailboxHdr)); w.mb_slot_elems = s->mb_slot_floats;
+                if (s->wtype == kWT_Q4_0) rc = launch_gemv_t<kWT_Q4_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
+                else                      rc = launch_gemv_t<kWT_Q8_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
+                if (rc) return rc;
             } else if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, w))) return rc;
         }
         cur = nxt;
@@ -491,7 +500,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         // pipeline hand-off: the activation leaves for the next slice's GPU right behind the last matmul
         s->send_pending = false;
         s->cur_class = 6;
-        int rc = launch_simple(s, k_peer_send, dim3(1, 1, 1), dim3(1024, 1, 1), 0, s->send_args);
+        int rc = launch_simple(s, k_peer_send, dim3(s->send_ctas, 1, 1), dim3(1024, 1, 1), 0, s->send_args);
         if (rc) return rc;
     }
     {
@@ -504,6 +513,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         s->cur_class = 6;
         prof_begin(s);
         if (s->cols) B200_CUDA(cudaLaunchKernelEx(&cfg, k_advance_cols, s->d_npast, s->cols, N));
+        else if (s->fold_send) B200_CUDA(cudaLaunchKernelEx(&cfg, k_advance_sent, s->d_npast + s->cur, N, (MailboxHdr *) s->mb_block));
         else         B200_CUDA(cudaLaunchKernelEx(&cfg, k_advance, s->d_npast + s->cur, N));
         prof_end(s);
         s->launches++;
@@ -1357,25 +1367,31 @@ static int pipeline_step_peer(b200_slice * s, const float * d_in, int n_rows, in
     const int r = s->pp_rank, W = s->pp_world;
     const size_t count = (size_t) n_rows * s->E;
     if (count > s->mb_slot_floats) return fail(B200_EINVAL, "hand-off of %zu floats exceeds the mailbox slot (%zu)", count, s->mb_slot_floats);
-    const bool recv_in = r > 0, sends = r < W - 1 || ring, recv_final = r == 0 && ring;
+    const bool recv_in = r > 0, sends = r < W - 1 || ring, recv_final = r == 0 && ring == 1;   // ring 2: rank 0 collects later
     MailboxHdr * mine = (MailboxHdr *) s->mb_block;
-    const float * inbox = (const float *)(s->mb_block + sizeof(MailboxHdr));
+    const uint2 * inbox = (const uint2 *)(s->mb_block + sizeof(MailboxHdr));
     PeerRecvArgs ra{mine, inbox, s->mb_slot_floats, &((MailboxHdr *) s->mb_prev)->ack, s->d_in, (int) count};
     PeerRecvArgs rf = ra; rf.dst = s->d_final;
-    PeerSendArgs sa{mine, (MailboxHdr *) s->mb_next, (float *)(s->mb_next + sizeof(MailboxHdr)), s->mb_slot_floats, s->d_out, (int) count};
+    PeerSendArgs sa{mine, (uint2 *)(s->mb_next + sizeof(MailboxHdr)), s->mb_slot_floats, s->d_out, (int) count};
+    const int xfer_ctas = (int) std::min<size_t>(32, (count + 8191) / 8192);      // one CTA per 8 K elements, at most 32
+    if (!sessions) { s->cur = session; s->cols = nullptr; }
+    // fold the send into the slice's last matmul for plain single-token steps of quantised, head-size-128 slices
+    const bool fold = s->use_fold && sends && !sessions && n_rows == 1 && s->D == 128 && s->wtype != kWT_F16 && s->use_ring && !s->use_nq &&
+                      !persist_applicable(s, 1) && !s->skip_attention;
     const float * in = recv_in ? s->d_in : d_in;
     int rc = 0;
-    if (!sessions) { s->cur = session; s->cols = nullptr; if (persist_applicable(s, n_rows) && (rc = persist_prepare(s, in, s->d_out))) return rc; }
+    if (!sessions && persist_applicable(s, n_rows) && (rc = persist_prepare(s, in, s->d_out))) return rc;
     auto body = [&]() -> int {
         int e;
         s->cur_class = 6;
-        if (recv_in && (e = launch_simple(s, k_peer_recv, dim3(1, 1, 1), dim3(1024, 1, 1), 0, ra))) return e;
-        if (sends) { s->send_args = sa; s->send_pending = true; }
+        if (recv_in && (e = launch_simple(s, k_peer_recv, dim3(xfer_ctas, 1, 1), dim3(1024, 1, 1), 0, ra))) return e;
+        if (sends && !fold) { s->send_args = sa; s->send_pending = true; s->send_ctas = xfer_ctas; }
+        s->fold_send = fold;
         e = enqueue_layers(s, in, n_rows, s->d_out);
-        s->send_pending = false;
+        s->send_pending = false; s->fold_send = false;
         if (e) return e;
         s->cur_class = 6;
-        if (recv_final && (e = launch_simple(s, k_peer_recv, dim3(1, 1, 1), dim3(1024, 1, 1), 0, rf))) return e;
+        if (recv_final && (e = launch_simple(s, k_peer_recv, dim3(xfer_ctas, 1, 1), dim3(1024, 1, 1), 0, rf))) return e;
         return 0;
     };
     B200_CUDA(cudaEventRecord(s->ev0, s->stream));
@@ -1389,8 +1405,7 @@ static int pipeline_step_peer(b200_slice * s, const float * d_in, int n_rows, in
         if (rc) return rc;
         for (int b = 0; b < n_rows; b++) s->past[sessions[b]] += 1;
     } else if (n_rows == 1 && s->use_graph && !s->profiling) {
-        s->cur = session; s->cols = nullptr;
-        GraphKey key{in, nullptr, (ring ? 1 : 0) | (session << 1)};
+        GraphKey key{in, nullptr, (ring & 3) | (fold ? 4 : 0) | (session << 3)};
         auto it = s->pp_graphs.find(key);
         if (it == s->pp_graphs.end()) {
             const int64_t before = s->launches;
@@ -1461,11 +1476,11 @@ static int pipeline_step_locked(b200_slice * s, const float * d_in, int n_rows, 
     } else if (ring && W > 1) {
         if ((rc = n.Send(s->d_out, count, kNcclFloat32, 0, s->nccl_comm, s->stream))) return nccl_fail("ncclSend", rc);
     }
-    if (r == 0 && ring && W > 1) {
+    if (r == 0 && ring == 1 && W > 1) {
         // the last slice's output comes back to the first rank (where the client-side lm_head lives)
         if ((rc = n.Recv(s->d_final, count, kNcclFloat32, W - 1, s->nccl_comm, s->stream))) return nccl_fail("ncclRecv", rc);
     }
-    s->launches += (r > 0) + (r < W - 1 || (ring && W > 1)) + (r == 0 && ring && W > 1);
+    s->launches += (r > 0) + (r < W - 1 || (ring && W > 1)) + (r == 0 && ring == 1 && W > 1);
     return 0;
 }
 
@@ -1493,16 +1508,19 @@ int b200_pipeline_mailbox_export(b200_slice_t * s, void * handle64) {
     if (!s || !handle64) return fail(B200_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(s->mu);
     B200_CUDA(cudaSetDevice(s->device));
+    s->mb_slot_floats = (size_t) s->n_ctx * s->E;
+    const size_t bytes = sizeof(MailboxHdr) + (size_t) kMbSlots * s->mb_slot_floats * 8;      // 8-byte {value, seq} elements
     if (!s->mb_block) {
-        s->mb_slot_floats = (size_t) s->n_ctx * s->E;
-        const size_t bytes = sizeof(MailboxHdr) + (size_t) kMbSlots * s->mb_slot_floats * 4;
         void * p = nullptr;
         B200_CUDA(cudaMalloc(&p, bytes));                 // a dedicated cudaMalloc block: IPC handles cover whole allocations
         s->allocs.push_back(p);
         s->mb_block = (uint8_t *) p;
-        B200_CUDA(cudaMemset(p, 0, sizeof(MailboxHdr)));
-        B200_CUDA(cudaDeviceSynchronize());
     }
+    // a fresh link: counters at zero, and sequence numbers start at 1, so a zeroed inbox holds no message
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    B200_CUDA(cudaMemset(s->mb_block, 0, bytes));
+    s->use_fold = env_int("B200_PP_FOLD", 1) != 0;
+    B200_CUDA(cudaDeviceSynchronize());
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t h;
     B200_CUDA(cudaIpcGetMemHandle(&h, s->mb_block));
@@ -1534,6 +1552,50 @@ int b200_pipeline_mailbox_connect(b200_slice_t * s, const void * handles, int nr
     return 0;
 }
 
+/* Measurement aid: `iters` bare hand-offs of n_rows rows around the ring with NO layers in between (rank 0: send, recv;
+ * others: recv, send), on the active transport; returns the device time per iteration in microseconds in *us_per_iter
+ * (one iteration = `world` hops).  Every rank must call it. */
+int b200_pipeline_pingpong(b200_slice_t * s, int n_rows, int iters, float * us_per_iter) {
+    if (!s || !s->nccl_comm || !us_per_iter) return fail(B200_EINVAL, "pipeline not initialised");
+    std::lock_guard<std::mutex> lk(s->mu);
+    B200_CUDA(cudaSetDevice(s->device));
+    const int r = s->pp_rank, W = s->pp_world;
+    const size_t count = (size_t) n_rows * s->E;
+    NcclApi & n = nccl();
+    MailboxHdr * mine = (MailboxHdr *) s->mb_block;
+    auto send = [&]() -> int {
+        if (s->mb_on) {
+            PeerSendArgs sa{mine, (uint2 *)(s->mb_next + sizeof(MailboxHdr)), s->mb_slot_floats, s->d_out, (int) count};
+            return launch_simple(s, k_peer_send, dim3((unsigned) std::min<size_t>(32, (count + 8191) / 8192), 1, 1), dim3(1024, 1, 1), 0, sa);
+        }
+        int rc = n.Send(s->d_out, count, kNcclFloat32, (r + 1) % W, s->nccl_comm, s->stream);
+        return rc ? nccl_fail("ncclSend", rc) : 0;
+    };
+    auto recv = [&]() -> int {
+        if (s->mb_on) {
+            PeerRecvArgs ra{mine, (const uint2 *)(s->mb_block + sizeof(MailboxHdr)), s->mb_slot_floats, &((MailboxHdr *) s->mb_prev)->ack, s->d_in, (int) count};
+            return launch_simple(s, k_peer_recv, dim3((unsigned) std::min<size_t>(32, (count + 8191) / 8192), 1, 1), dim3(1024, 1, 1), 0, ra);
+        }
+        int rc = n.Recv(s->d_in, count, kNcclFloat32, (r + W - 1) % W, s->nccl_comm, s->stream);
+        return rc ? nccl_fail("ncclRecv", rc) : 0;
+    };
+    cudaEvent_t e0, e1;
+    B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+    int rc = 0;
+    for (int it = 0; it < iters + 8 && !rc; it++) {
+        if (it == 8) cudaEventRecord(e0, s->stream);
+        if (r == 0) { rc = send(); if (!rc) rc = recv(); }
+        else        { rc = recv(); if (!rc) rc = send(); }
+    }
+    cudaEventRecord(e1, s->stream);
+    cudaStreamSynchronize(s->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *us_per_iter = 1e3f * ms / (float) iters;
+    return rc;
+}
+
 /* 1 when steps use the peer-memory mailboxes, 0 when they use ncclSend / ncclRecv. */
 int b200_pipeline_transport(b200_slice_t * s) { return s && s->mb_on ? 1 : 0; }
 
@@ -1555,6 +1617,33 @@ int b200_pipeline_error(b200_slice_t * s) {
     int err = 0;
     cudaMemcpy(&err, s->mb_block + offsetof(MailboxHdr, err), 4, cudaMemcpyDeviceToHost);
     return err;
+}
+
+/* Rank 0: receive one final activation ([n_rows][n_embd]) that a step issued with ring = 2 left in flight, into d_dst
+ * (NULL: the buffer b200_pipeline_result() returns).  Results arrive in the order the steps were issued.  Other ranks: no-op.
+ * This is what keeps every slice busy in throughput mode: rank 0 issues steps for sessions k, k+1, ... back to back and
+ * collects session k's result only when it needs it (rank r then works on session k while rank r+1 works on k-1). */
+int b200_pipeline_collect(b200_slice_t * s, int n_rows, float * d_dst) {
+    if (!s || !s->nccl_comm) return fail(B200_EINVAL, "pipeline not initialised");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->pp_rank != 0 || s->pp_world < 2) return 0;
+    if (n_rows <= 0 || n_rows > s->n_ctx) return fail(B200_EINVAL, "n_rows %d outside [1, n_ctx]", n_rows);
+    B200_CUDA(cudaSetDevice(s->device));
+    float * dst = d_dst ? d_dst : s->d_final;
+    const size_t count = (size_t) n_rows * s->E;
+    if (s->mb_on) {
+        PeerRecvArgs rf{(MailboxHdr *) s->mb_block, (const uint2 *)(s->mb_block + sizeof(MailboxHdr)), s->mb_slot_floats,
+                        &((MailboxHdr *) s->mb_prev)->ack, dst, (int) count};
+        s->cur_class = 6;
+        int rc = launch_simple(s, k_peer_recv, dim3((unsigned) std::min<size_t>(32, (count + 8191) / 8192), 1, 1), dim3(1024, 1, 1), 0, rf);
+        if (rc) return rc;
+    } else {
+        NcclApi & n = nccl();
+        int rc = n.Recv(dst, count, kNcclFloat32, s->pp_world - 1, s->nccl_comm, s->stream);
+        if (rc) return nccl_fail("ncclRecv", rc);
+        s->launches++;
+    }
+    return 0;
 }
 
 /* Device pointer of the pipeline's final activation on rank 0 (valid after a `ring` step), else dev_out. */

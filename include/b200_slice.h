@@ -162,8 +162,9 @@ int b200_pipeline_init(b200_slice_t * s, int rank, int nranks, const void * id12
 
 /* One pipeline step on this rank: rank 0 takes `d_in` (device, may be NULL on other ranks), every
  * rank r>0 receives [n_tokens][n_embd] from r-1, runs its layers, and sends to r+1; the last rank
- * leaves the result in its dev_out buffer and, when `ring` != 0, also sends it to rank 0 (which
- * receives it into the buffer b200_pipeline_result() returns), closing the token loop. Asynchronous on the slice's stream. */
+ * leaves the result in its dev_out buffer and, when `ring` != 0, also sends it to rank 0 (ring = 1: rank 0
+ * receives it inside this step into the buffer b200_pipeline_result() returns, closing the token loop; ring = 2: rank 0
+ * collects it later, see b200_pipeline_collect). Asynchronous on the slice's stream. */
 int b200_pipeline_step(b200_slice_t * s, const float * d_in, int n_tokens, int ring);
 /* The same hand-off for one session, and for a batched step (one token for each listed session: [n_seq][n_embd] moves
  * between the slices).  Every rank passes the same session list. */
@@ -179,7 +180,14 @@ int b200_pipeline_mailbox_export(b200_slice_t * s, void * handle64);
 int b200_pipeline_mailbox_connect(b200_slice_t * s, const void * handles /* nranks x 64 bytes, rank order */, int nranks);
 int b200_pipeline_transport(b200_slice_t * s);   /* 1 = peer mailboxes, 0 = NCCL */
 int b200_pipeline_set_transport(b200_slice_t * s, int peer);   /* all ranks alike; 1 only after a successful connect */
+/* Measurement aid: bare hand-offs around the ring, no layers; device microseconds per iteration (= nranks hops). */
+int b200_pipeline_pingpong(b200_slice_t * s, int n_rows, int iters, float * us_per_iter);
 int b200_pipeline_error(b200_slice_t * s);       /* non-zero: a mailbox poll timed out (8 s) on this rank */
+
+/* Throughput mode (BASELINE config 5): a step issued with ring = 2 sends the last slice's output to rank 0 but rank 0 does
+ * not wait for it inside the step; it collects the results later, in issue order, with b200_pipeline_collect (rank 0 only;
+ * a no-op elsewhere).  Rank 0 can so issue steps for several sessions back to back and every slice stays busy. */
+int b200_pipeline_collect(b200_slice_t * s, int n_rows, float * d_dst /* NULL: the pipeline result buffer */);
 
 /* Device pointer of the pipeline's final activation: on rank 0 after a ring step the last slice's output, else dev_out. */
 float * b200_pipeline_result(b200_slice_t * s);

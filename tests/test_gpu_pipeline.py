@@ -99,16 +99,16 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("peer", [1, 0], ids=["peer-mailbox", "nccl"])
-def test_two_gpu_pipeline_bit_exact(tmp_path, peer):
+@pytest.mark.parametrize("peer,fold", [(1, 1), (1, 0), (0, 0)], ids=["peer-folded-into-matmuls", "peer-send-recv-kernels", "nccl"])
+def test_two_gpu_pipeline_bit_exact(tmp_path, peer, fold):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT, "tmp": str(tmp_path)})
-    env = dict(os.environ, B200_PP_PEER=str(peer))
+    env = dict(os.environ, B200_PP_PEER=str(peer), B200_PP_FOLD=str(fold))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", str(29533 + peer), str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(29533 + 2 * peer + fold), str(script)],
                          capture_output=True, text=True, timeout=600, env=env)
     assert "PIPELINE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
     assert ("transport=peer" if peer else "transport=nccl") in out.stdout, out.stdout[-500:]
