@@ -585,6 +585,9 @@ def _h2d(sl, x: np.ndarray):
     x = np.ascontiguousarray(x, np.float32)
     rc = _cudart().cudaMemcpy(C.c_void_p(sl.dev_in), C.c_void_p(x.ctypes.data), C.c_size_t(x.nbytes), 1)
     assert rc == 0, rc
+    # a cudaMemcpy from PAGEABLE memory returns once the source is staged; the DMA of the tail (> 1 MiB) may still be in
+    # flight, and the slice's stream is non-blocking, i.e. not ordered behind the legacy stream: wait for the device
+    assert _cudart().cudaDeviceSynchronize() == 0
 
 
 def _d2h(sl, out: np.ndarray):

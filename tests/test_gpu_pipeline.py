@@ -31,7 +31,13 @@ bcast, gather = torch_collectives(dist, torch.device("cuda", local))
 want_peer = os.environ.get("B200_PP_PEER", "1") != "0"
 transport = join_pipeline(sl, rank, world, bcast, gather, peer=want_peer)
 lib.b200_pipeline_result.restype = C.c_void_p; lib.b200_pipeline_result.argtypes = [C.c_void_p]
-cudart = C.CDLL("libcudart.so.12")
+_rt = C.CDLL("libcudart.so.12")
+class _Rt:                                   # cudaMemcpy from pageable memory may return before the DMA tail lands, and the
+    def cudaMemcpy(self, *a):                # slice stream is non-blocking (not ordered behind the legacy stream): sync
+        rc = _rt.cudaMemcpy(*a)
+        _rt.cudaDeviceSynchronize()
+        return rc
+cudart = _Rt()
 rng = np.random.default_rng(21)
 ok = True
 if rank == 0:
