@@ -172,10 +172,28 @@ def config5():
                 g = groups[i - LAG]
                 collect(len(g), out_row(g[0]))
 
+    # steady state, the way a generation loop runs: session k's next token is issued as soon as ITS previous result is
+    # back, so the pipeline never drains between rounds (each call = `rounds` tokens for every session / group)
+    def steady(n_items, issue, gather, rounds):
+        total = n_items * rounds
+        win = min(LAG, n_items)
+        for j in range(total + win):
+            if rank == 0 and j >= win:
+                gather((j - win) % n_items)
+            if j < total:
+                issue(j % n_items)
+
+    def steady_sessions(rounds):
+        steady(S, lambda k: step_session(k, 1, 2, row(k)), lambda k: collect(1, out_row(k)), rounds)
+
+    def steady_groups(rounds):
+        steady(G, lambda g: step_batch(groups[g], 2, row(groups[g][0])), lambda g: collect(len(groups[g]), out_row(groups[g][0])), rounds)
+
     # ---- parity: pipelined modes vs the serial mode, same tokens, same positions (3 rounds each, rewound in between)
     R = 3
     outs = {}
-    for name, fn in (("serial", None), ("batched", round_batched), ("pipelined", round_pipelined), ("pipelined_groups", round_pipelined_groups)):
+    for name, fn in (("serial", None), ("batched", round_batched), ("pipelined", round_pipelined), ("pipelined_groups", round_pipelined_groups),
+                     ("steady_sessions", steady_sessions), ("steady_groups", steady_groups)):
         rewind_all(PRE)
         barrier(sl)
         rec = np.zeros((R, S, E), np.float32)
@@ -191,6 +209,12 @@ def config5():
                 sl.sync()
                 if rank == 0:
                     rec[r_] = d2h(result_ptr(), (S, E))
+            elif name.startswith("steady"):
+                if r_ == R - 1:                  # R tokens per session in ONE pipelined run; only the last round's outputs remain
+                    fn(R)
+                    sl.sync()
+                    if rank == 0:
+                        rec[r_] = res.cpu().numpy() if world > 1 else 0
             else:
                 fn()
                 sl.sync()
@@ -205,6 +229,9 @@ def config5():
             if world == 1 and name != "batched":
                 continue
             parity[name + "_vs_serial_mismatching_floats"] = int((outs[name].view(np.uint32) != outs["serial"].view(np.uint32)).sum())
+        for name in ("steady_sessions", "steady_groups"):
+            if world > 1:                        # the last of R tokens per session, produced without ever draining the pipeline
+                parity[name + "_vs_serial_mismatching_floats"] = int((outs[name][R - 1].view(np.uint32) != outs["serial"][R - 1].view(np.uint32)).sum())
         parity["checked_floats_per_mode"] = int(outs["serial"].size)
     # session 0's first serial step against the compiled reference over the slice files (prompt + 1 token)
     if rank == 0 and not os.environ.get("CFG5_NO_REF"):
@@ -231,6 +258,13 @@ def config5():
             fn()
         ms = timed(sl, fn, K)
         modes[name] = {"ms_per_round": ms, "tokens_per_s": S * 1e3 / ms}
+    if world > 1:
+        for name, fn in (("steady_sessions", steady_sessions), ("steady_groups", steady_groups)):
+            rewind_all(PRE)
+            fn(2)
+            ms = timed(sl, lambda: fn(K), 1) / K
+            modes[name] = {"ms_per_round": ms, "tokens_per_s": S * 1e3 / ms,
+                           "note": "%d tokens per session in one pipelined run, a session's next token issued when its previous result is back" % K}
     err = lib.b200_pipeline_error(h) if world > 1 else 0
     info = sl.info
     out = None
