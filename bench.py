@@ -41,10 +41,27 @@ N_CTX = 512
 PREFILL = 256
 SEED = 0
 FALLBACK_HBM_GBS = 6650.0
-# dram__bytes_read.sum + dram__bytes_write.sum per k_gemv launch, averaged over the 4 launches of a layer, from the
-# ncu --set full capture committed under profiles/ (None until that capture exists for the current kernels)
-NCU_TRAFFIC_PER_LAUNCH = 30.5e6     # profiles/r01_decode_kernels_ncu_full.md, two layers: reads (28.4 + 9.47 + 50.8 + 26.0) MB + writes (~7.4 MB of dirty
-                                    # activation / KV lines written back while w1|w3 streams) per layer / 4 launches; algorithmic 28.47e6 (no re-reads)
+NCU_CAPTURE = os.path.join(ROOT, "profiles", "r02_decode_kernels_ncu_full.md")
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_gemv launch, averaged over the launches of the committed
+    `ncu --set full` capture of a decode step (profiles/r02_decode_kernels_ncu_full.md, produced by scripts/summarize_ncu.py
+    from the .ncu-rep): parsed here, not a constant.  Returns (read + write bytes, read bytes, launches) or (None, None, 0)."""
+    try:
+        rd = wr = n = 0
+        cols = None
+        for line in open(NCU_CAPTURE):
+            f = [x.strip() for x in line.strip().strip("|").split("|")]
+            if "dram_rd_MB" in f:
+                cols = {name: i for i, name in enumerate(f)}
+            elif cols and f and f[0].startswith("void k_gemv<"):
+                rd += float(f[cols["dram_rd_MB"]]) * 1e6
+                wr += float(f[cols["dram_wr_MB"]]) * 1e6
+                n += 1
+        return ((rd + wr) / n, rd / n, n) if n else (None, None, 0)
+    except Exception:
+        return None, None, 0
 
 
 def model_dir() -> str:
@@ -431,13 +448,24 @@ def run_b200(args):
                         "note": "launches overlap under programmatic dependent launch, so per-class times can sum to more than the step"}
         except Exception as ex:
             in_graph = {"error": repr(ex)}
+        traffic, traffic_rd, traffic_n = ncu_traffic_per_launch()
+        replay = {"achieved": achieved, "frac": achieved / peak, "avg_launch_us": 1e3 * only_ms / n_gemv,
+                  "timing": "two CUDA events on the slice's stream around %d graph replays of the step's %d k_gemv launches with the "
+                            "attention launch skipped (b200_debug_skip_attention): the matmul kernels back to back" % (reps, n_gemv)}
+        in_step = in_graph if isinstance(in_graph, dict) and "achieved" in in_graph else None
         roof = {"bound": "hbm", "kernel": "k_gemv (Q4_0xQ8_0 exact-mode weight matmul; qkv, wo, w1|w3, w2 = 4 launches/layer)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": NCU_TRAFFIC_PER_LAUNCH,
-                "timing": "two CUDA events on the slice's stream around %d graph replays of the step's %d k_gemv launches "
-                          "(attention skipped), L2 cold for weights (3.6 GB per replay)" % (reps, n_gemv),
+                # the dominant kernel AS IT RUNS INSIDE THE STEP (the replayed decode graph, programmatic dependent launch and
+                # all): launch duration = last CTA exit - first CTA entry from in-kernel %globaltimer stamps
+                "achieved": in_step["achieved"] if in_step else achieved, "peak": peak, "unit": "GB/s",
+                "frac": (in_step["achieved"] if in_step else achieved) / peak, "peak_source": peak_src,
+                "traffic": traffic, "traffic_read_only": traffic_rd,
+                "traffic_source": "profiles/r02_decode_kernels_ncu_full.md: dram__bytes_read.sum + dram__bytes_write.sum averaged over its "
+                                  "%d k_gemv launches (ncu --set full, one decode step, cold caches)" % traffic_n,
+                "timing": ("in-step: %globaltimer stamps of every k_gemv launch inside the replayed decode graph, last of 3 steps"
+                           if in_step else "matmul-only graph replay (in-step stamps unavailable)"),
                 "algorithmic_bytes_per_launch": wbytes / n_gemv,
-                "avg_launch_us": 1e3 * only_ms / n_gemv,
+                "avg_launch_us": (in_step["gemv_us_per_token"] / n_gemv) if in_step else 1e3 * only_ms / n_gemv,
+                "matmul_only_replay": replay,
                 "event_bracketed": {"achieved": ev_achieved, "frac": ev_achieved / peak,
                                     "note": "one CUDA-event pair per launch, un-graphed: includes ~4 us of event overhead per launch"},
                 "share_of_step": gemv_ms / float(ms.sum()),

@@ -761,6 +761,144 @@ __global__ void __launch_bounds__(256) k_gemv_f16(const GemvF16Args a) {
     }
 }
 
+// K1f-ring: the same F16 matmul fed by 1-D TMA bulk copies (single-token steps).  The warp-per-row kernel above starts
+// its weight stream only after its RMSNorm prologue and keeps at most a few KB per warp in flight; here
+//   * a producer warp streams every consumer warp's rows through that warp's OWN ring of shared-memory stages
+//     (kF16Stage bytes = kF16Stage / 512 groups of 8 chunks, contiguous in the packed row), starting BEFORE
+//     griddepcontrol.wait -- weights never depend on the previous kernel -- so the stream runs through the prologue and
+//     across the kernel boundary (programmatic dependent launch, trigger after the last copy is issued);
+//   * the activation row is normalised once per CTA, rounded to fp16 (ggml_fp32_to_fp16_row) and stored WIDENED BACK to f32
+//     in the weights' [c8][lane] permutation (two conflict-free planes of 4 chunks), so the 8 activations of a 16-byte
+//     weight word are two LDS.128 and the inner loop is one F16->F32 conversion + one FFMA per weight (the ncu capture
+//     of the warp-per-row kernel showed ~8 instructions per weight and 45-57 % issue utilisation: it was issue-bound);
+//   * rows are whole groups of 8 chunks (K % 256 == 0: every LLaMA shape); other K use the kernel above;
+//   * arithmetic unchanged: lane = slot, FMA chain in chunk order, fixed reduce tree, double tail (ggml.c:2323-2357).
+constexpr int kF16Stage = 2048;                  // bytes per ring stage: 4 groups of 8 chunks of one row
+constexpr int kF16Warps = 8;
+
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(kF16Warps * 32 + 32) k_gemv_f16_ring(const GemvF16Args a, int NS) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int K = a.K, nchunk = K / 32, nc8 = (nchunk + 7) / 8;
+    const int row_bytes = nc8 * 512;
+    const int n_stage = (row_bytes + kF16Stage - 1) / kF16Stage;         // stages per row (the last one may be short)
+    constexpr int NM = (EPI == EPI_GATE) ? 2 : 1;
+    // smem: [ring kF16Warps * NS * kF16Stage][xf: 2 planes x nc8 * 32 lanes x 4 f32][full kF16Warps*NS][empty kF16Warps*NS][red 8 doubles]
+    uint8_t * ring = smem;
+    float * xf = (float *)(smem + (size_t) kF16Warps * NS * kF16Stage);
+    uint64_t * full = (uint64_t *)((uint8_t *) xf + (size_t) nc8 * 1024);
+    uint64_t * empty = full + kF16Warps * NS;
+    double * red = (double *)(empty + kF16Warps * NS);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col = blockIdx.y;
+    const int n_tiles = (a.rows + kF16Warps - 1) / kF16Warps;
+    if (tid == 0) {
+        for (int i = 0; i < kF16Warps * NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kF16Warps) {
+        // ------------------------------------------------------------------ producer: lane w feeds consumer warp w
+        if (lane < kF16Warps) {
+            uint8_t * ring_w = ring + (size_t) lane * NS * kF16Stage;
+            uint64_t * full_w = full + lane * NS, * empty_w = empty + lane * NS;
+            int slot = 0, use = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int row = tile * kF16Warps + lane;
+                if (row >= a.rows) continue;
+                #pragma unroll 1
+                for (int m = 0; m < NM; m++) {
+                    const uint8_t * src = (const uint8_t *)((m ? a.W2 : a.W) + (size_t) row * nc8 * 256);
+                    for (int st = 0; st < n_stage; st++) {
+                        const uint32_t bytes = (uint32_t) min(kF16Stage, row_bytes - st * kF16Stage);
+                        if (use > 0) mbar_wait(&empty_w[slot], (use - 1) & 1);
+                        mbar_arrive_expect_tx(&full_w[slot], bytes);
+                        bulk_g2s(ring_w + (size_t) slot * kF16Stage, src + (size_t) st * kF16Stage, bytes, &full_w[slot]);
+                        if (++slot == NS) { slot = 0; use++; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    grid_dep_wait();
+    // after the wait (the ordering guarantee k_attn128's pre-wait prefetch relies on, see k_gemv): the next kernel's CTAs may
+    // become resident as this kernel's CTAs drain and start THEIR weight stream
+    if (tid == 0) grid_dep_launch();
+    const float * x = a.x + (size_t) col * a.ldx;
+    float scale = 1.0f;
+    if (PRO == PRO_NORM) {
+        double s = 0.0;
+        for (int i = tid; i < K; i += kF16Warps * 32) s += (double) fmul(x[i], x[i]);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp] = s;
+        named_bar_sync(1, kF16Warps * 32);
+        double tot = 0.0;
+        for (int i = 0; i < kF16Warps; i++) tot += red[i];
+        scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) K), 1e-6f)));
+    }
+    for (int i = tid; i < nc8 * 256; i += kF16Warps * 32) {
+        // chunk c = 8 * c8 + j of slot l (element x[c * 32 + l]) -> plane j >> 2, [c8][l][j & 3]
+        const int c8 = i >> 8, l = (i >> 3) & 31, j = i & 7, c = c8 * 8 + j;
+        float v = x[c * 32 + l];
+        if (PRO == PRO_NORM) v = fmul(fmul(v, scale), a.norm_w[c * 32 + l]);
+        xf[(size_t)(j >> 2) * nc8 * 128 + (c8 * 32 + l) * 4 + (j & 3)] = h2f(f2h(v));
+    }
+    named_bar_sync(1, kF16Warps * 32);
+
+    const uint8_t * ring_w = ring + (size_t) warp * NS * kF16Stage;
+    uint64_t * full_w = full + warp * NS, * empty_w = empty + warp * NS;
+    int slot = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row = tile * kF16Warps + warp;
+        if (row >= a.rows) continue;
+        float res[2] = {0.f, 0.f};
+        #pragma unroll 1
+        for (int m = 0; m < NM; m++) {
+            float acc = 0.f;
+            for (int st = 0; st < n_stage; st++) {
+                mbar_wait(&full_w[slot], phase);
+                const uint4 * wp = (const uint4 *)(ring_w + (size_t) slot * kF16Stage) + lane;
+                const float4 * xa = (const float4 *) xf + (size_t) st * (kF16Stage / 512) * 32 + lane;
+                const float4 * xb = xa + (size_t) nc8 * 32;
+                const int g_n = min(kF16Stage / 512, nc8 - st * (kF16Stage / 512));
+                #pragma unroll
+                for (int g = 0; g < kF16Stage / 512; g++) {
+                    if (g < g_n) {
+                        const uint4 wv = wp[g * 32];
+                        const float4 x0 = xa[g * 32], x1 = xb[g * 32];
+                        const float2 w01 = __half22float2(*(const __half2 *) &wv.x), w23 = __half22float2(*(const __half2 *) &wv.y);
+                        const float2 w45 = __half22float2(*(const __half2 *) &wv.z), w67 = __half22float2(*(const __half2 *) &wv.w);
+                        acc = ffma(w01.x, x0.x, acc); acc = ffma(w01.y, x0.y, acc);
+                        acc = ffma(w23.x, x0.z, acc); acc = ffma(w23.y, x0.w, acc);
+                        acc = ffma(w45.x, x1.x, acc); acc = ffma(w45.y, x1.y, acc);
+                        acc = ffma(w67.x, x1.z, acc); acc = ffma(w67.y, x1.w, acc);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_w[slot]);
+                if (++slot == NS) { slot = 0; phase ^= 1; }
+            }
+            // slots s = 8*j + l: (x0+x2)+(x1+x3) -> xor 16, xor 8; lo128+hi128 -> xor 4; hadd, hadd -> xor 1, xor 2
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 16));
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 8));
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+            acc = fadd(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+            res[m] = (float)(double) acc;                       // K % 32 == 0 on this path: no double-precision tail
+        }
+        if (lane == 0) {
+            float v = res[0];
+            if (EPI == EPI_RESID) v = fadd(v, a.resid[(size_t) col * a.ldr + row]);
+            if (EPI == EPI_GATE)  v = fmul(h2f(a.tsilu[f2h(res[0])]), res[1]);
+            a.y[(size_t) col * a.ldy + row] = v;
+        }
+    }
+}
+
 // repack F16 weights [rows][K] -> [rows][nc8][32 lanes][8 chunks] (+ tail [rows][K%32])
 __global__ void k_repack_f16(const uint16_t * src, uint16_t * dst, uint16_t * tail, int rows, int K) {
     const int nchunk = K / 32, nc8 = (nchunk + 7) / 8, ntail = K & 31;
@@ -1070,39 +1208,51 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
             #pragma unroll
             for (int e = 0; e < 8; e++) qf[c][e] = h2f(q16s[32 * c + 8 * ql + e]);
         const int nloc = 8 * ((tcount + 31) >> 5);
-        for (int i = sub; i < nloc; i += 64) {
-            const int t = 32 * (i >> 3) + 8 * g + (i & 7);
-            const bool valid = t < tcount;
-            const uint16_t * krow = (FUSE && t == pos) ? k16s : (i < npf ? (const uint16_t *)(Ks + (size_t) i * kAttnRow)
-                                                                          : kc + (size_t) t * E + h * 128);
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                uint4 kv[4];
+        // two positions per thread per iteration: 8 x 16-byte loads in flight (rows past the staged window are L2 / HBM reads)
+        for (int i0 = sub; i0 < nloc; i0 += 128) {
+            uint4 kv[2][4];
+            bool valid[2];
+            int tt[2];
+            #pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = i0 + 64 * u;
+                const int t = 32 * (i >> 3) + 8 * g + (i & 7);
+                tt[u] = t;
+                valid[u] = i < nloc && t < tcount;
+                const uint16_t * krow = (FUSE && t == pos) ? k16s : (i < npf ? (const uint16_t *)(Ks + (size_t) i * kAttnRow)
+                                                                              : kc + (size_t) t * E + h * 128);
                 #pragma unroll
-                for (int c = 0; c < 4; c++) kv[c] = *(const uint4 *)(krow + 32 * c + 8 * ql);
-                #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const uint32_t u[4] = {kv[c].x, kv[c].y, kv[c].z, kv[c].w};
+                for (int c = 0; c < 4; c++) kv[u][c] = valid[u] ? *(const uint4 *)(krow + 32 * c + 8 * ql) : make_uint4(0, 0, 0, 0);
+            }
+            #pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (i0 + 64 * u >= nloc) break;                      // uniform across the warp: i0 + 64 u is < nloc for all lanes or none
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (valid[u]) {
                     #pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const uint16_t kh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
-                        acc[e] = ffma(h2f(kh), qf[c][e], acc[e]);
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t w4[4] = {kv[u][c].x, kv[u][c].y, kv[u][c].z, kv[u][c].w};
+                        #pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const uint16_t kh = (uint16_t)(w4[e >> 1] >> (16 * (e & 1)));
+                            acc[e] = ffma(h2f(kh), qf[c][e], acc[e]);
+                        }
                     }
                 }
-            }
-            float v8[8];
-            #pragma unroll
-            for (int e = 0; e < 8; e++) {                            // (x0 + x2) + (x1 + x3)
-                float x = fadd(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], 2));
-                v8[e] = fadd(x, __shfl_xor_sync(0xffffffffu, x, 1));
-            }
-            const float t0 = fadd(v8[0], v8[4]), t1 = fadd(v8[1], v8[5]), t2 = fadd(v8[2], v8[6]), t3 = fadd(v8[3], v8[7]);
-            const float dot = fadd(fadd(t0, t1), fadd(t2, t3));
-            if (valid && ql == 0) {
-                // scores meet in every CTA's shared memory (distributed shared memory), not in an L2 scratch
-                const float sv = fmul(dot, a.kq_scale);
+                float v8[8];
                 #pragma unroll
-                for (int rnk = 0; rnk < 4; rnk++) dsmem_st(dsmem_addr(sc + t, rnk), sv);
+                for (int e = 0; e < 8; e++) {                            // (x0 + x2) + (x1 + x3)
+                    float x = fadd(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], 2));
+                    v8[e] = fadd(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                }
+                const float t0 = fadd(v8[0], v8[4]), t1 = fadd(v8[1], v8[5]), t2 = fadd(v8[2], v8[6]), t3 = fadd(v8[3], v8[7]);
+                const float dot = fadd(fadd(t0, t1), fadd(t2, t3));
+                if (valid[u] && ql == 0) {
+                    // scores meet in every CTA's shared memory (distributed shared memory), not in an L2 scratch
+                    const float sv = fmul(dot, a.kq_scale);
+                    #pragma unroll
+                    for (int rnk = 0; rnk < 4; rnk++) dsmem_st(dsmem_addr(sc + tt[u], rnk), sv);
+                }
             }
         }
     }
@@ -1143,17 +1293,30 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
     if (tid < 128) {
         const int l = tid >> 4, cg = tid & 15;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int t = 8 * g + l; t < lim; t += 32) {
-            const int i = ((t >> 5) << 3) + l;
-            const uint16_t * vrow = (FUSE && t == pos) ? v16s : (i < npf ? (const uint16_t *)(Vs + (size_t) i * kAttnRow)
-                                                                          : vc + (size_t) t * E + h * 128);
-            const uint4 vv = *(const uint4 *)(vrow + 8 * cg);
-            const uint32_t u[4] = {vv.x, vv.y, vv.z, vv.w};
-            const float p = h2f(p16[t]);
+        // four value rows in flight per thread (rows past the staged window come from L2 / HBM: one dependent-looking load
+        // per iteration made this loop 13 us at T ~ 1000); the FMAs stay in position order
+        for (int tb = 8 * g + l; tb < lim; tb += 128) {
+            uint4 vv4[4];
             #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const uint16_t vh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
-                acc[e] = ffma(h2f(vh), p, acc[e]);
+            for (int u = 0; u < 4; u++) {
+                const int t = tb + 32 * u;
+                const int i = ((t >> 5) << 3) + l;
+                const uint16_t * vrow = (FUSE && t == pos) ? v16s : (i < npf ? (const uint16_t *)(Vs + (size_t) i * kAttnRow)
+                                                                              : vc + (size_t) t * E + h * 128);
+                vv4[u] = t < lim ? *(const uint4 *)(vrow + 8 * cg) : make_uint4(0, 0, 0, 0);
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int t = tb + 32 * u;
+                if (t < lim) {
+                    const uint32_t u4[4] = {vv4[u].x, vv4[u].y, vv4[u].z, vv4[u].w};
+                    const float p = h2f(p16[t]);
+                    #pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const uint16_t vh = (uint16_t)(u4[e >> 1] >> (16 * (e & 1)));
+                        acc[e] = ffma(h2f(vh), p, acc[e]);
+                    }
+                }
             }
         }
         // channels 8cg..8cg+7 are finished by CTA cg >> 2: drop the slot partials straight into its shared memory

@@ -64,7 +64,7 @@ struct b200_slice {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
     int64_t launches = 0, weight_bytes = 0;
-    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true;
+    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true, f16_ring = true;
     bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
     int opt_ns = 0, opt_cta_per_sm = 0, opt_nc = 0, opt_pre = 3, opt_nomath = 0;   // read once at load (environment)
@@ -221,6 +221,36 @@ static int launch_f16(b200_slice * s, GemvF16Args a) {
     if (!attr_set[s->device & 15]) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         attr_set[s->device & 15] = true;
+    }
+    if (a.N == 1 && s->use_ring && s->f16_ring && (a.K & 255) == 0) {
+        // single-token steps: TMA-ring variant (weights stream from before the dependency wait, two CTAs per SM)
+        auto rk = k_gemv_f16_ring<PRO, EPI>;
+        static bool rattr[16] = {false};
+        if (!rattr[s->device & 15]) {
+            B200_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            B200_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            rattr[s->device & 15] = true;
+        }
+        const int nc8 = (a.K / 32 + 7) / 8;
+        const size_t fixed = (size_t) nc8 * 1024 + 64 + 64;
+        int NS = s->opt_ns > 0 ? s->opt_ns : (int)(((size_t) 112 * 1024 - fixed) / ((size_t) kF16Warps * (kF16Stage + 16)));
+        if (NS < 2) NS = 2;
+        if (NS > 12) NS = 12;
+        const size_t rsmem = (size_t) kF16Warps * NS * kF16Stage + (size_t) nc8 * 1024 + (size_t) 2 * kF16Warps * NS * 8 + 64;
+        const int n_tiles = (a.rows + kF16Warps - 1) / kF16Warps;
+        int per_sm = (int)(kSmemLimit / (rsmem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+        int rgx = n_tiles < s->n_sm * per_sm ? n_tiles : s->n_sm * per_sm;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(rgx, 1, 1); cfg.blockDim = dim3(kF16Warps * 32 + 32, 1, 1); cfg.dynamicSmemBytes = rsmem; cfg.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+        prof_begin(s);
+        B200_CUDA(cudaLaunchKernelEx(&cfg, rk, a, NS));
+        prof_end(s);
+        s->launches++;
+        return 0;
     }
     int gx = (a.rows + 7) / 8;
     const int cap = s->n_sm * 8;
@@ -1006,6 +1036,7 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
     s->opt_ns = env_int("B200_NS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
     s->opt_pre = env_int("B200_PRE", 3); s->opt_nomath = env_int("B200_DBG_NOMATH", 0);
+    s->f16_ring = env_int("B200_F16_RING", 1) != 0;          // F16-weight slices: TMA-ring matmul for single-token steps
     s->use_persist = env_int("B200_PERSIST", 0) != 0;         // single-token step as ONE persistent kernel (persist.cuh)
     s->persist_tr = env_int("B200_PERSIST_TR", 4); s->persist_ns = env_int("B200_PERSIST_NS", 0); s->persist_ctas = env_int("B200_PERSIST_CTAS", 0);
     if (s->persist_tr != 1 && s->persist_tr != 2 && s->persist_tr != 4) s->persist_tr = 4;
