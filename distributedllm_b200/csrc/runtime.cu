@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "persist.cuh"
 #include "fastgemm.cuh"
+#include "fastgemm2.cuh"
 #include "ggjt_file.hpp"
 
 #include <algorithm>
@@ -67,6 +68,7 @@ struct b200_slice {
     bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true, f16_ring = true;
     bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
+    int fast_version = 2;                                                               // 2: fastgemm2.cuh (TMA tensor map, N = 256), 1: fastgemm.cuh
     int opt_ns = 0, opt_cta_per_sm = 0, opt_nc = 0, opt_pre = 3, opt_nomath = 0;   // read once at load (environment)
     float ema_token_ms = 0.f;              // host-buffer decode calls: smoothed device time of one token (sleep-then-poll wait)
     std::mutex mu;
@@ -284,6 +286,65 @@ static int launch_fast_gemm(b200_slice * s, const PackedW & W, const float * res
     return launch_simple(s, kern, dim3((groups + 15) / 16, (N + kFgN - 1) / kFgN, 1), dim3(160, 1, 1), kFgSmem, a);
 }
 
+// second-generation tcgen05 prefill matmul (fastgemm2.cuh): 128 x 256 tiles, activations through a tensor-map TMA
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encode() {
+    static TensorMapEncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void * p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (TensorMapEncodeFn) p;
+    });
+    return fn;
+}
+
+template <int WT, int EPI>
+static int launch_fast_gemm2_t(b200_slice * s, const PackedW & W, const float * resid, int ldr, float * y, int ldy, int N, int out_rows) {
+    TensorMapEncodeFn enc = tensor_map_encode();
+    if (!enc) return fail(B200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    // activations xh [N][K] fp16, K innermost; box = 64 halfs (128 B, the swizzle span) x 256 token rows; rows >= N read as zeros
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t) W.K, (cuuint64_t) N};
+    const cuuint64_t strides[1] = {(cuuint64_t) W.K * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t) kF2N};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *) s->xh, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(B200_ECUDA, "cuTensorMapEncodeTiled failed (%d) for K=%d N=%d", (int) cr, W.K, N);
+    auto kern = k_gemm_tc2<WT, EPI>;
+    static bool attr_set[16] = {false};
+    if (!attr_set[s->device & 15]) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, f2_smem(WT)));
+        attr_set[s->device & 15] = true;
+    }
+    FastGemm2Args a{}; a.W = W; a.resid = resid; a.ldr = ldr; a.y = y; a.ldy = ldy; a.N = N; a.out_rows = out_rows; a.tsilu = s->tsilu;
+    const int groups = W.n_tiles * W.TR;                     // 8-row groups in packed order
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((groups + 15) / 16, (N + kF2N - 1) / kF2N, 1); cfg.blockDim = dim3(kF2Threads, 1, 1);
+    cfg.dynamicSmemBytes = f2_smem(WT); cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+    prof_begin(s);
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, a, map));
+    prof_end(s);
+    s->launches++;
+    return 0;
+}
+template <int EPI>
+static int launch_fast_any(b200_slice * s, const PackedW & W, const float * resid, int ldr, float * y, int ldy, int N, int out_rows) {
+    if (s->fast_version >= 2) {
+        if (W.wtype == kWT_Q4_0) return launch_fast_gemm2_t<kWT_Q4_0, EPI>(s, W, resid, ldr, y, ldy, N, out_rows);
+        return launch_fast_gemm2_t<kWT_Q8_0, EPI>(s, W, resid, ldr, y, ldy, N, out_rows);
+    }
+    return launch_fast_gemm<EPI>(s, W, resid, ldr, y, ldy, N, out_rows);
+}
+
 // ---------------------------------------------------------------- persistent single-token step (persist.cuh)
 static bool persist_applicable(const b200_slice * s, int N) {
     return s->use_persist && N == 1 && !s->cols && s->D == 128 && (s->wtype == kWT_Q4_0 || s->wtype == kWT_Q8_0) && !s->skip_attention &&
@@ -380,7 +441,8 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
     for (int il = 0; il < (persist ? 0 : s->L); il++) {
         LayerW & Lw = s->layers[il];
         // grid-barrier norm+quant epilogue: decode only (every CTA of wo / w2 must be co-resident: 1 tile per CTA)
-        const bool fast = s->fast_prefill && N >= s->fast_min_tokens && s->wtype == kWT_Q4_0 && (Lw.qkv.n_tiles * Lw.qkv.TR) % 16 == 0 &&
+        const bool fast = s->fast_prefill && N >= s->fast_min_tokens && (s->wtype == kWT_Q4_0 || (s->wtype == kWT_Q8_0 && s->fast_version >= 2)) &&
+                          (Lw.qkv.n_tiles * Lw.qkv.TR) % 16 == 0 &&
                           (Lw.wo.n_tiles * Lw.wo.TR) % 16 == 0 && (Lw.w13.n_tiles * Lw.w13.TR) % 16 == 0;
         const bool nq = s->use_nq && N == 1 && !s->cols && s->wtype != kWT_F16 && Lw.wo.n_tiles <= 256 && Lw.wo.n_tiles <= s->n_sm * 2;
         float * nxt = (il == s->L - 1) ? out : ((il & 1) ? s->xb : s->xa);
@@ -396,7 +458,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             f.W = Lw.f_q; f.y = s->qkv;         if ((rc = launch_f16<PRO_NORM, EPI_STORE>(s, f))) return rc;
         } else if (fast) {
             if ((rc = launch_prep<true>(s, cur, E, Lw.attn_norm, E, N))) return rc;
-            if ((rc = launch_fast_gemm<FG_STORE>(s, Lw.qkv, nullptr, 0, s->qkv, 3 * E, N, 3 * E))) return rc;
+            if ((rc = launch_fast_any<FG_STORE>(s, Lw.qkv, nullptr, 0, s->qkv, 3 * E, N, 3 * E))) return rc;
         } else {
             GemvArgs g{}; g.W = Lw.qkv; g.x = cur; g.ldx = E; g.norm_w = Lw.attn_norm; g.y = s->qkv; g.ldy = 3 * E;
             g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x;
@@ -479,13 +541,13 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
         } else if (fast) {
             s->cur_class = 3;
             if ((rc = launch_prep<false>(s, s->att, E, nullptr, E, N))) return rc;
-            if ((rc = launch_fast_gemm<FG_RESID>(s, Lw.wo, cur, E, s->ffin, E, N, E))) return rc;
+            if ((rc = launch_fast_any<FG_RESID>(s, Lw.wo, cur, E, s->ffin, E, N, E))) return rc;
             s->cur_class = 4;
             if ((rc = launch_prep<true>(s, s->ffin, E, Lw.ffn_norm, E, N))) return rc;
-            if ((rc = launch_fast_gemm<FG_GATE>(s, Lw.w13, nullptr, 0, s->gate, FF, N, FF))) return rc;
+            if ((rc = launch_fast_any<FG_GATE>(s, Lw.w13, nullptr, 0, s->gate, FF, N, FF))) return rc;
             s->cur_class = 5;
             if ((rc = launch_prep<false>(s, s->gate, FF, nullptr, FF, N))) return rc;
-            if ((rc = launch_fast_gemm<FG_RESID>(s, Lw.w2, s->ffin, E, nxt, E, N, E))) return rc;
+            if ((rc = launch_fast_any<FG_RESID>(s, Lw.w2, s->ffin, E, nxt, E, N, E))) return rc;
         } else {
             const float dsc = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
             s->cur_class = 3;
@@ -1033,6 +1095,7 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->use_graph = env_int("B200_GRAPH", 1) != 0;
     s->use_pdl   = env_int("B200_PDL", 1) != 0;
     s->fast_prefill = env_int("B200_FAST_PREFILL", 0) != 0; s->fast_min_tokens = env_int("B200_FAST_MIN_TOKENS", 32);
+    s->fast_version = env_int("B200_FAST_V", 2);
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
     s->opt_ns = env_int("B200_NS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
     s->opt_pre = env_int("B200_PRE", 3); s->opt_nomath = env_int("B200_DBG_NOMATH", 0);

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from distributedllm_b200 import capi
 import bench
-L = int(os.environ.get("PROF_LAYERS", "4")); N = int(os.environ.get("PROF_TOKENS", "256"))
+L = int(os.environ.get("PROF_LAYERS", "4")); N = int(os.environ.get("PROF_TOKENS", "512"))
 path = bench.slice_file("7b", 0, L - 1)
 sl = capi.Slice(path, 0, 512)
 x = bench.synth_inputs(N, sl.n_embd, 1)

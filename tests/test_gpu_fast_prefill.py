@@ -17,11 +17,14 @@ from distributedllm_b200 import ggjt
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n_tokens", [128, 200, 33])
-def test_fast_prefill_close_to_exact(tmp_models, n_tokens):
+@pytest.mark.parametrize("version,wtype", [(2, ggjt.T_Q4_0), (2, ggjt.T_Q8_0), (1, ggjt.T_Q4_0)],
+                         ids=["v2-tma-n256-q4_0", "v2-tma-n256-q8_0", "v1-q4_0"])
+@pytest.mark.parametrize("n_tokens", [128, 200, 33, 300])
+def test_fast_prefill_close_to_exact(tmp_models, monkeypatch, n_tokens, version, wtype):
     from distributedllm_b200 import capi
+    monkeypatch.setenv("B200_FAST_V", str(version))
     sh = ggjt.SHAPES["tiny128b"]
-    path = tmp_models("tiny128b", ggjt.T_Q4_0, 0, 1)
+    path = tmp_models("tiny128b", wtype, 0, 1)
     x = np.random.default_rng(4).standard_normal((n_tokens, sh.n_embd), dtype=np.float32)
     exact = capi.Slice(path, 0, 512)
     fast = capi.Slice(path, 0, 512)
@@ -43,10 +46,12 @@ def test_fast_prefill_close_to_exact(tmp_models, n_tokens):
     fast.close()
 
 
-def test_tensor_core_matmul_alone_is_tight(tmp_models):
+@pytest.mark.parametrize("version,wtype", [(2, ggjt.T_Q4_0), (2, ggjt.T_Q8_0), (1, ggjt.T_Q4_0)])
+def test_tensor_core_matmul_alone_is_tight(tmp_models, monkeypatch, version, wtype):
     from distributedllm_b200 import capi
+    monkeypatch.setenv("B200_FAST_V", str(version))
     sh = ggjt.SHAPES["tiny128b"]
-    path = tmp_models("tiny128b", ggjt.T_Q4_0, 0, 0)
+    path = tmp_models("tiny128b", wtype, 0, 0)
     x = np.random.default_rng(4).standard_normal((128, sh.n_embd), dtype=np.float32)
     a, b = capi.Slice(path, 0, 512), capi.Slice(path, 0, 512)
     b.set_fast_prefill(True, 32)
