@@ -20,15 +20,14 @@
 
 namespace b200 {
 
-constexpr int kF2M = 128, kF2N = 256, kF2K = 128;
-constexpr int kF2Stages = 2;
+constexpr int kF2M = 128, kF2K = 128;                      // token-tile width NT = 256 (wide matrices) or 128 (narrow ones: twice the CTAs)
 constexpr int kF2DqWarps = 8;
 constexpr int kF2Threads = (kF2DqWarps + 2) * 32;          // + TMA warp + MMA warp
 constexpr int kF2ABytes = kF2M * kF2K * 2;                  // 32 KB: two [128 x 64] K-major SW128 sub-tiles
-constexpr int kF2BBytes = kF2N * kF2K * 2;                  // 64 KB: two [256 x 64] sub-tiles
 __host__ __device__ constexpr int f2_raw_bytes(int wt) { return 16 * chunk_bytes(wt); }                   // one quad of 128 rows
-__host__ __device__ constexpr int f2_stage_bytes(int wt) { return ((f2_raw_bytes(wt) + 1023) & ~1023) + kF2ABytes + kF2BBytes; }
-__host__ __device__ constexpr int f2_smem(int wt) { return kF2Stages * f2_stage_bytes(wt) + 128; }   // Q8_0: 231 552 of 232 448 B
+__host__ __device__ constexpr int f2_stage_bytes(int wt, int nt) { return ((f2_raw_bytes(wt) + 1023) & ~1023) + kF2ABytes + nt * kF2K * 2; }
+__host__ __device__ constexpr int f2_stages(int wt, int nt) { return (nt == 128 && wt == kWT_Q4_0) ? 3 : 2; }
+__host__ __device__ constexpr int f2_smem(int wt, int nt) { return f2_stages(wt, nt) * f2_stage_bytes(wt, nt) + 128; }   // Q8_0, NT 256: 231 552 of 232 448 B
 
 struct FastGemm2Args {
     PackedW W;
@@ -43,14 +42,15 @@ __device__ __forceinline__ void tma_load_2d(void * dst, const CUtensorMap * map,
                  :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int WT, int EPI>
+template <int WT, int EPI, int NT>
 __global__ void __launch_bounds__(kF2Threads, 1) k_gemm_tc2(const FastGemm2Args a, const __grid_constant__ CUtensorMap xmap) {
     constexpr int CB = (WT == kWT_Q4_0) ? kQ4Chunk : kQ8Chunk;
+    constexpr int kF2N = NT, kF2BBytes = NT * kF2K * 2, kF2Stages = f2_stages(WT, NT);
     constexpr int RAW = 16 * CB, RAWP = (RAW + 1023) & ~1023, STAGE = RAWP + kF2ABytes + kF2BBytes;
     extern __shared__ __align__(1024) uint8_t smem[];       // SWIZZLE_128B tiles need 1 KB alignment (no static shared memory in this kernel)
     uint64_t * bars = (uint64_t *)(smem + kF2Stages * STAGE);
-    uint64_t * tma_full = bars, * a_full = bars + 2, * stage_free = bars + 4, * acc_full = bars + 6;
-    uint32_t * tmem_slot = (uint32_t *)(bars + 8);
+    uint64_t * tma_full = bars, * a_full = bars + 3, * stage_free = bars + 6, * acc_full = bars + 9;
+    uint32_t * tmem_slot = (uint32_t *)(bars + 10);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mt = blockIdx.x, nt = blockIdx.y;             // 128-row tile, 256-token tile
     const int nbq = a.W.nbq;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) k_gemm_tc2(const FastGemm2Args 
         mbar_fence_init();
     }
     if (warp == kF2DqWarps + 1) {                           // TMEM: 256 columns of fp32 accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "n"(NT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -179,10 +179,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) k_gemm_tc2(const FastGemm2Args 
         // -------------------------------------------------------------------- epilogue: TMEM -> registers -> global
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int q = warp & 3, half = warp >> 2;            // TMEM lane quarter of this warp; which 128 token columns
+        const int q = warp & 3, half = warp >> 2;            // TMEM lane quarter of this warp; which half of the token columns
         const int m = q * 32 + lane;                         // accumulator lane = row within the M tile (packed order)
         #pragma unroll 1
-        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
+        for (int c0 = half * (NT / 2); c0 < half * (NT / 2) + NT / 2; c0 += 16) {
             uint32_t v[16];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t) c0;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) k_gemm_tc2(const FastGemm2Args 
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == kF2DqWarps + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem_base) : "memory");
+    if (warp == kF2DqWarps + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(NT) : "memory");
 }
 
 }  // namespace b200

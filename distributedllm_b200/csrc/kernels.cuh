@@ -1409,6 +1409,171 @@ __global__ void __launch_bounds__(1024) k_peer_send(const PeerSendArgs a) {
     }
 }
 
+// =============================================================================================
+// K5t: attention for MULTI-token calls (prompt chunks), head size 128, query-TILED ("flash-style" staging, exact arithmetic).
+// k_attn128<false> launches one cluster per (head, query): every query re-reads its head's K and V rows from L2 --
+// 4.3 GB per layer for a 512-token prompt, 1.27 ms per layer, 70 % of a tensor-core prefill.  Here one CTA owns a head and
+// kAttnQB = 16 consecutive queries: the head's K rows are staged in shared memory ONCE, all 16 queries score against them,
+// one warp per query runs the softmax, then the V rows replace the K rows and every query accumulates against them.
+// Per query the arithmetic is k_attn128's, operand for operand:
+//   scores   4 lanes per position, lane ql owns the 16-byte vectors m = ql + 4c; (x0+x2)+(x1+x3), fixed 8-slot tree
+//   softmax  max, fp16 exp table, sum in double (exact in any order), p = fp16(e * (float)(1/S))
+//   V.p      32 f32 slots per channel (slot = t mod 32, vector j = slot / 8 -> warp-quad g), positions in ascending order,
+//            ((p0+p2)+(p1+p3)) per slot, the 8-slot tree, the (T mod 32) tail in double -- T = n_past + N of the CALL
+// Needs T = n_past + N <= kAttnTMax staged rows (139 KB); longer contexts keep the per-query cluster kernel.
+// =============================================================================================
+constexpr int kAttnQB = 16;
+constexpr int kAttnTMax = 512;
+
+struct AttnTiledArgs {
+    const uint16_t * q16; const uint16_t * kc; const uint16_t * vc;
+    const int * n_past; int E, H, N;
+    const uint16_t * texp;
+    float * out;                                   // [N][E]
+    int * aq_out; float * da_out; int out_nbq; float out_dscale;
+    float kq_scale;
+    int t_rows, t_pad;                             // staged rows (>= n_past + N) and the padded score row length
+};
+
+__global__ void __launch_bounds__(512) k_attn128_tiled(const AttnTiledArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    if (threadIdx.x == 0) grid_dep_launch();
+    grid_dep_wait();
+    const int h = blockIdx.x, n0 = blockIdx.y * kAttnQB, E = a.E;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_past = *a.n_past, T = n_past + a.N;
+    const int nq = min(kAttnQB, a.N - n0);                               // queries of this block
+    const int tmax = n_past + n0 + nq;                                   // positions the block's last query sees
+    uint8_t * KV = smem;                                                 // [t_rows][kAttnRow]
+    float * sc = (float *)(smem + (size_t) a.t_rows * kAttnRow);         // [QB][t_pad]
+    uint16_t * p16 = (uint16_t *)(sc + (size_t) kAttnQB * a.t_pad);      // [QB][t_pad]
+    float * partl = (float *)(p16 + (size_t) kAttnQB * a.t_pad);         // [4][8][128]
+    uint16_t * q16s = (uint16_t *)(partl + 4 * 8 * 128);                 // [QB][128]
+
+    // ---- stage the head's key rows t < tmax and the block's query rows
+    for (int idx = tid; idx < tmax * 16; idx += 512) {
+        const int t = idx >> 4, ch = idx & 15;
+        cp_async16(KV + (size_t) t * kAttnRow + ch * 16, a.kc + (size_t) t * E + h * 128 + ch * 8);
+    }
+    for (int idx = tid; idx < nq * 16; idx += 512) {
+        const int q = idx >> 4, ch = idx & 15;
+        cp_async16(q16s + q * 128 + ch * 8, a.q16 + (size_t)(n0 + q) * E + h * 128 + ch * 8);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- scores: 128 positions per pass, 4 lanes per position
+    {
+        const int ql = tid & 3;
+        for (int q = 0; q < nq; q++) {
+            const int tcount = n_past + n0 + q + 1;
+            float qf[4][8];
+            #pragma unroll
+            for (int c = 0; c < 4; c++)
+                #pragma unroll
+                for (int e = 0; e < 8; e++) qf[c][e] = h2f(q16s[q * 128 + 32 * c + 8 * ql + e]);
+            for (int t0 = 0; t0 < tcount; t0 += 128) {
+                const int t = t0 + (tid >> 2);
+                const bool valid = t < tcount;
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+                    const uint16_t * krow = (const uint16_t *)(KV + (size_t) t * kAttnRow);
+                    uint4 kv[4];
+                    #pragma unroll
+                    for (int c = 0; c < 4; c++) kv[c] = *(const uint4 *)(krow + 32 * c + 8 * ql);
+                    #pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t u[4] = {kv[c].x, kv[c].y, kv[c].z, kv[c].w};
+                        #pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            const uint16_t kh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
+                            acc[e] = ffma(h2f(kh), qf[c][e], acc[e]);
+                        }
+                    }
+                }
+                float v8[8];
+                #pragma unroll
+                for (int e = 0; e < 8; e++) {                            // (x0 + x2) + (x1 + x3)
+                    float x = fadd(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], 2));
+                    v8[e] = fadd(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                }
+                const float u0 = fadd(v8[0], v8[4]), u1 = fadd(v8[1], v8[5]), u2 = fadd(v8[2], v8[6]), u3 = fadd(v8[3], v8[7]);
+                const float dot = fadd(fadd(u0, u1), fadd(u2, u3));
+                if (valid && ql == 0) sc[(size_t) q * a.t_pad + t] = fmul(dot, a.kq_scale);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- softmax: warp q owns query q; meanwhile the value rows replace the key rows
+    for (int idx = tid; idx < tmax * 16; idx += 512) {
+        const int t = idx >> 4, ch = idx & 15;
+        cp_async16(KV + (size_t) t * kAttnRow + ch * 16, a.vc + (size_t) t * E + h * 128 + ch * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (warp < nq) {
+        const int q = warp, tcount = n_past + n0 + q + 1;
+        float * s_q = sc + (size_t) q * a.t_pad;
+        uint16_t * p_q = p16 + (size_t) q * a.t_pad;
+        float mx = -INFINITY;
+        for (int t = lane; t < tcount; t += 32) mx = fmaxf(mx, s_q[t]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double s = 0.0;
+        for (int t = lane; t < tcount; t += 32) {
+            const float e = h2f(a.texp[f2h(fsub(s_q[t], mx))]);
+            s_q[t] = e; s += (double) e;
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);      // fp16-valued terms: exact in any order
+        const float inv = (float)(1.0 / s);
+        for (int t = lane; t < tcount; t += 32) p_q[t] = f2h(fmul(s_q[t], inv));
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- V . p, one query at a time, all 512 threads: quad g = slot vector, thread (l, cg) = slot 8g + l, channels 8cg..8cg+7
+    const int npT = T & ~31;
+    const int g = tid >> 7, l = (tid >> 4) & 7, cg = tid & 15;
+    for (int q = 0; q < nq; q++) {
+        const int n = n0 + q, tcount = n_past + n + 1, lim = min(npT, tcount);
+        const uint16_t * p_q = p16 + (size_t) q * a.t_pad;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = 8 * g + l; t < lim; t += 32) {
+            const uint4 vv = *(const uint4 *)(KV + (size_t) t * kAttnRow + cg * 16);
+            const uint32_t u[4] = {vv.x, vv.y, vv.z, vv.w};
+            const float p = h2f(p_q[t]);
+            #pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint16_t vh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
+                acc[e] = ffma(h2f(vh), p, acc[e]);
+            }
+        }
+        float4 * dst = (float4 *)(partl + (g * 8 + l) * 128 + 8 * cg);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        __syncthreads();
+        if (tid < 128) {
+            const int c = tid;
+            float vv[8];
+            #pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float p0 = partl[(0 * 8 + k) * 128 + c], p1 = partl[(1 * 8 + k) * 128 + c];
+                const float p2 = partl[(2 * 8 + k) * 128 + c], p3 = partl[(3 * 8 + k) * 128 + c];
+                vv[k] = fadd(fadd(p0, p2), fadd(p1, p3));
+            }
+            const float t0 = fadd(vv[0], vv[4]), t1 = fadd(vv[1], vv[5]), t2 = fadd(vv[2], vv[6]), t3 = fadd(vv[3], vv[7]);
+            double sumf = (double) fadd(fadd(t0, t1), fadd(t2, t3));
+            for (int t = npT; t < tcount; t++)
+                sumf += (double) fmul(h2f(((const uint16_t *)(KV + (size_t) t * kAttnRow))[c]), h2f(p_q[t]));
+            const float ov = (float) sumf;
+            a.out[(size_t) n * E + h * 128 + c] = ov;
+            // channels [32 w, 32 w + 32) of head h are Q8_0 block 4 h + w of the wo matmul's input
+            if (a.aq_out) warp_quant_block(ov, lane, a.aq_out + (size_t) n * a.out_nbq * 32, a.da_out + (size_t) n * a.out_nbq * 4,
+                                           4 * h + warp, a.out_dscale);
+        }
+        __syncthreads();
+    }
+}
+
 // position counter kept on the device so a captured graph can be replayed for every token
 __global__ void k_advance(int * n_past, int by) { grid_dep_wait(); if (threadIdx.x == 0) *n_past += by; }
 // the same for a pipelined slice whose LAST matmul stored its rows into the next rank's inbox (EPI_RESID_SEND): the message

@@ -65,7 +65,7 @@ struct b200_slice {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
     int64_t launches = 0, weight_bytes = 0;
-    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true, f16_ring = true;
+    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true, f16_ring = true, use_tiled_attn = true;
     bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
     int fast_version = 2;                                                               // 2: fastgemm2.cuh (TMA tensor map, N = 256), 1: fastgemm.cuh
@@ -302,7 +302,7 @@ static TensorMapEncodeFn tensor_map_encode() {
     return fn;
 }
 
-template <int WT, int EPI>
+template <int WT, int EPI, int NT>
 static int launch_fast_gemm2_t(b200_slice * s, const PackedW & W, const float * resid, int ldr, float * y, int ldy, int N, int out_rows) {
     TensorMapEncodeFn enc = tensor_map_encode();
     if (!enc) return fail(B200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -310,22 +310,22 @@ static int launch_fast_gemm2_t(b200_slice * s, const PackedW & W, const float * 
     CUtensorMap map;
     const cuuint64_t dims[2] = {(cuuint64_t) W.K, (cuuint64_t) N};
     const cuuint64_t strides[1] = {(cuuint64_t) W.K * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t) kF2N};
+    const cuuint32_t box[2] = {64, (cuuint32_t) NT};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *) s->xh, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(B200_ECUDA, "cuTensorMapEncodeTiled failed (%d) for K=%d N=%d", (int) cr, W.K, N);
-    auto kern = k_gemm_tc2<WT, EPI>;
+    auto kern = k_gemm_tc2<WT, EPI, NT>;
     static bool attr_set[16] = {false};
     if (!attr_set[s->device & 15]) {
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, f2_smem(WT)));
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, f2_smem(WT, NT)));
         attr_set[s->device & 15] = true;
     }
     FastGemm2Args a{}; a.W = W; a.resid = resid; a.ldr = ldr; a.y = y; a.ldy = ldy; a.N = N; a.out_rows = out_rows; a.tsilu = s->tsilu;
     const int groups = W.n_tiles * W.TR;                     // 8-row groups in packed order
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((groups + 15) / 16, (N + kF2N - 1) / kF2N, 1); cfg.blockDim = dim3(kF2Threads, 1, 1);
-    cfg.dynamicSmemBytes = f2_smem(WT); cfg.stream = s->stream;
+    cfg.gridDim = dim3((groups + 15) / 16, (N + NT - 1) / NT, 1); cfg.blockDim = dim3(kF2Threads, 1, 1);
+    cfg.dynamicSmemBytes = f2_smem(WT, NT); cfg.stream = s->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -339,8 +339,14 @@ static int launch_fast_gemm2_t(b200_slice * s, const PackedW & W, const float * 
 template <int EPI>
 static int launch_fast_any(b200_slice * s, const PackedW & W, const float * resid, int ldr, float * y, int ldy, int N, int out_rows) {
     if (s->fast_version >= 2) {
-        if (W.wtype == kWT_Q4_0) return launch_fast_gemm2_t<kWT_Q4_0, EPI>(s, W, resid, ldr, y, ldy, N, out_rows);
-        return launch_fast_gemm2_t<kWT_Q8_0, EPI>(s, W, resid, ldr, y, ldy, N, out_rows);
+        // 256-token tiles halve the dequantisation per flop; a matrix whose 128-row tiles x 256-token tiles would leave SMs idle
+        // (wo, w2: 32 row tiles) takes 128-token tiles and three stages instead
+        const int mtiles = (W.n_tiles * W.TR + 15) / 16;
+        const bool wide = (long long) mtiles * ((N + 255) / 256) >= s->n_sm || N <= 128;
+        if (W.wtype == kWT_Q4_0) return wide ? launch_fast_gemm2_t<kWT_Q4_0, EPI, 256>(s, W, resid, ldr, y, ldy, N, out_rows)
+                                             : launch_fast_gemm2_t<kWT_Q4_0, EPI, 128>(s, W, resid, ldr, y, ldy, N, out_rows);
+        return wide ? launch_fast_gemm2_t<kWT_Q8_0, EPI, 256>(s, W, resid, ldr, y, ldy, N, out_rows)
+                    : launch_fast_gemm2_t<kWT_Q8_0, EPI, 128>(s, W, resid, ldr, y, ldy, N, out_rows);
     }
     return launch_fast_gemm<EPI>(s, W, resid, ldr, y, ldy, N, out_rows);
 }
@@ -505,6 +511,24 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
                 if (s->trace && s->trace_next < 512) { aa.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(2); s->trace_ctas.push_back(4 * H); }
                 aa.lut_smem = 1;
                 if ((rc = launch_simple(s, k_attn128<true>, dim3(4 * H, 1, 1), dim3(256, 1, 1), asm_lut, aa))) return rc;
+            } else if (s->use_tiled_attn && s->past[s->cur] + N <= kAttnTMax) {
+                // prompt chunk whose whole context fits the staged window: query-tiled kernel, K / V read once per 16 queries
+                s->cur_class = 1;
+                RopeArgs ra{s->qkv, E, H, D, N, d_npast, s->cs, s->q16, kc, vc, nullptr, 0};
+                if ((rc = launch_simple(s, k_rope_append, dim3((E / 2 + 255) / 256, N, 1), dim3(256, 1, 1), 0, ra))) return rc;
+                s->cur_class = 2;
+                const int Tn = s->past[s->cur] + N;
+                AttnTiledArgs ta{};
+                ta.q16 = s->q16; ta.kc = kc; ta.vc = vc; ta.n_past = d_npast; ta.E = E; ta.H = H; ta.N = N; ta.texp = s->texp; ta.out = s->att;
+                if (preq) { ta.aq_out = s->aq_att; ta.da_out = s->da_att; ta.out_nbq = s->nbqE; ta.out_dscale = dsc; }
+                ta.kq_scale = aa.kq_scale; ta.t_rows = Tn; ta.t_pad = (Tn + 31) & ~31;
+                const size_t tsm = (size_t) ta.t_rows * kAttnRow + (size_t) kAttnQB * ta.t_pad * 6 + 4 * 8 * 128 * 4 + kAttnQB * 256 + 64;
+                static bool tattr[16] = {false};
+                if (!tattr[s->device & 15]) {
+                    B200_CUDA(cudaFuncSetAttribute(k_attn128_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+                    tattr[s->device & 15] = true;
+                }
+                if ((rc = launch_simple(s, k_attn128_tiled, dim3(H, (N + kAttnQB - 1) / kAttnQB, 1), dim3(512, 1, 1), tsm, ta))) return rc;
             } else {
                 s->cur_class = 1;
                 RopeArgs ra{s->qkv, E, H, D, N, d_npast, s->cs, s->q16, kc, vc, nullptr, 0};
@@ -1099,6 +1123,7 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
     s->opt_ns = env_int("B200_NS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
     s->opt_pre = env_int("B200_PRE", 3); s->opt_nomath = env_int("B200_DBG_NOMATH", 0);
+    s->use_tiled_attn = env_int("B200_TILED_ATTN", 1) != 0;  // prompt chunks: query-tiled attention (K / V staged once per 16 queries)
     s->f16_ring = env_int("B200_F16_RING", 1) != 0;          // F16-weight slices: TMA-ring matmul for single-token steps
     s->use_persist = env_int("B200_PERSIST", 0) != 0;         // single-token step as ONE persistent kernel (persist.cuh)
     s->persist_tr = env_int("B200_PERSIST_TR", 4); s->persist_ns = env_int("B200_PERSIST_NS", 0); s->persist_ctas = env_int("B200_PERSIST_CTAS", 0);

@@ -142,3 +142,23 @@ def test_edge_cases_empty_ragged_and_full_context(tmp_models):
     for r in (ref, ref2, ref3):
         r.close()
     gpu.close()
+
+
+@pytest.mark.parametrize("tiled", [1, 0], ids=["query-tiled", "cluster-per-query"])
+def test_both_prompt_attention_kernels_are_exact(tmp_models, monkeypatch, tiled):
+    """Prompt chunks of head-size-128 models run the query-tiled kernel (K / V staged once per 16 queries) while the whole
+    context fits its 512-row window, the per-query cluster kernel beyond; both must be the oracle's arithmetic.  Ragged
+    chunks: T crosses multiples of 32 inside a call, a 1-token call in between, a chunk that is not a multiple of 16."""
+    monkeypatch.setenv("B200_TILED_ATTN", str(tiled))
+    sh = ggjt.SHAPES["tiny128"]
+    path = tmp_models("tiny128", ggjt.T_Q4_0, 0, 2, seed=17)
+    bad, tot = _run_pair(path, [37, 1, 70, 5, 16, 33, 200, 64], sh, n_ctx=512, seed=3)
+    assert bad == 0, "%d of %d floats differ" % (bad, tot)
+
+
+def test_prompt_attention_beyond_the_staged_window(tmp_models):
+    """n_ctx 1024: chunks that end beyond position 512 fall back to the cluster kernel mid-prompt; still exact."""
+    sh = ggjt.SHAPES["tiny128"]
+    path = tmp_models("tiny128", ggjt.T_Q4_0, 0, 1, seed=18)
+    bad, tot = _run_pair(path, [300, 200, 40, 1, 100], sh, n_ctx=1024, seed=4)
+    assert bad == 0, "%d of %d floats differ" % (bad, tot)
