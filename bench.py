@@ -563,6 +563,35 @@ def run_b200(args):
             parity = {"error": repr(ex)}
         barrier()
 
+    # ---- prompt throughput of the same model (not the headline metric): one 512-token call, device-resident, exact mode and the
+    # opt-in tcgen05 fast mode (K2: dequant fused into a TMA-fed tcgen05 / TMEM tile kernel; tolerance-level parity)
+    prefill = None
+    if world == 1:
+        try:
+            x512 = synth_inputs(N_CTX, E, 3)
+            _h2d(sl, x512)
+            prefill, outs = {}, {}
+            for name, fast in (("exact", False), ("tcgen05_fast", True)):
+                sl.set_fast_prefill(fast, 32)
+                for rep in range(2):
+                    sl.clear_context()
+                    sl.mark(0)
+                    sl.forward_device(sl.dev_in, N_CTX, sl.dev_out)
+                    sl.mark(1)
+                    sl.sync()
+                prefill[name + "_tokens_per_s"] = N_CTX / (sl.mark_elapsed_ms() / 1e3)
+                o = np.empty((N_CTX, E), np.float32)
+                _d2h(sl, o)
+                outs[name] = o
+            sl.set_fast_prefill(False, 32)
+            sl.clear_context()
+            d = outs["tcgen05_fast"] - outs["exact"]
+            prefill["fast_vs_exact_rel_rms"] = float(np.sqrt(np.mean(d * d)) / np.sqrt(np.mean(outs["exact"] ** 2)))
+            prefill["what"] = ("one %d-token prompt call through all 32 layers, activations resident in HBM; fast mode = fp16 tensor-core "
+                               "matmuls (fastgemm2.cuh), off by default, decode is always exact" % N_CTX)
+        except Exception as ex:
+            prefill = {"error": repr(ex)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -581,7 +610,7 @@ def run_b200(args):
                            "l2": "no flush: each step streams %.2f GB of weights, 29x the 126 MB L2" % (W_all / 1e9),
                            "timing": "CUDA events on the slice's stream around %d steps; wall %.1f ms" % (K, wall_ms)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "step_roofline": step_roof,
-                "tokens_per_s_at_p511": at_p511["tokens_per_s"], "at_p511": at_p511,
+                "tokens_per_s_at_p511": at_p511["tokens_per_s"], "at_p511": at_p511, "prefill": prefill,
                 "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1447,7 +1447,7 @@ __global__ void __launch_bounds__(512) k_attn128_tiled(const AttnTiledArgs a) {
     uint8_t * KV = smem;                                                 // [t_rows][kAttnRow]
     float * sc = (float *)(smem + (size_t) a.t_rows * kAttnRow);         // [QB][t_pad]
     uint16_t * p16 = (uint16_t *)(sc + (size_t) kAttnQB * a.t_pad);      // [QB][t_pad]
-    float * partl = (float *)(p16 + (size_t) kAttnQB * a.t_pad);         // [4][8][128]
+    float * partl = (float *)(p16 + (size_t) kAttnQB * a.t_pad);         // [4 groups][8 slots][128 channels]
     uint16_t * q16s = (uint16_t *)(partl + 4 * 8 * 128);                 // [QB][128]
 
     // ---- stage the head's key rows t < tmax and the block's query rows
@@ -1530,47 +1530,60 @@ __global__ void __launch_bounds__(512) k_attn128_tiled(const AttnTiledArgs a) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    // ---- V . p, one query at a time, all 512 threads: quad g = slot vector, thread (l, cg) = slot 8g + l, channels 8cg..8cg+7
+    // ---- V . p: FOUR queries at a time, one per 128-thread group.  Thread (l, cg) of a group walks all four slot vectors
+    // j = 0..3 of its slot l (positions 32k + 8j + l, ascending per slot) for channels 8cg..8cg+7, adds them as the AVX reduce
+    // does -- (j0 + j2) + (j1 + j3) -- in registers, and only the 8-slot tree crosses threads (group-local shared memory).
     const int npT = T & ~31;
-    const int g = tid >> 7, l = (tid >> 4) & 7, cg = tid & 15;
-    for (int q = 0; q < nq; q++) {
-        const int n = n0 + q, tcount = n_past + n + 1, lim = min(npT, tcount);
+    const int grp = tid >> 7, gt = tid & 127, l = gt >> 4, cg = gt & 15;
+    float * part_g = partl + grp * (8 * 128);                            // [8 slots][128 channels] of this group
+    for (int q0 = 0; q0 < nq; q0 += 4) {
+        const int q = q0 + grp;
+        const bool live = q < nq;
+        const int n = n0 + q, tcount = n_past + n + 1, lim = live ? min(npT, tcount) : 0;
         const uint16_t * p_q = p16 + (size_t) q * a.t_pad;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int t = 8 * g + l; t < lim; t += 32) {
-            const uint4 vv = *(const uint4 *)(KV + (size_t) t * kAttnRow + cg * 16);
-            const uint32_t u[4] = {vv.x, vv.y, vv.z, vv.w};
-            const float p = h2f(p_q[t]);
+        float acc[4][8];
+        #pragma unroll
+        for (int j = 0; j < 4; j++)
             #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const uint16_t vh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
-                acc[e] = ffma(h2f(vh), p, acc[e]);
+            for (int e = 0; e < 8; e++) acc[j][e] = 0.f;
+        for (int tb = l; tb < lim; tb += 32) {
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int t = tb + 8 * j;
+                if (t < lim) {
+                    const uint4 vv = *(const uint4 *)(KV + (size_t) t * kAttnRow + cg * 16);
+                    const uint32_t u[4] = {vv.x, vv.y, vv.z, vv.w};
+                    const float p = h2f(p_q[t]);
+                    #pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const uint16_t vh = (uint16_t)(u[e >> 1] >> (16 * (e & 1)));
+                        acc[j][e] = ffma(h2f(vh), p, acc[j][e]);
+                    }
+                }
             }
         }
-        float4 * dst = (float4 *)(partl + (g * 8 + l) * 128 + 8 * cg);
-        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        __syncthreads();
-        if (tid < 128) {
-            const int c = tid;
+        float4 * dst = (float4 *)(part_g + l * 128 + 8 * cg);
+        dst[0] = make_float4(fadd(fadd(acc[0][0], acc[2][0]), fadd(acc[1][0], acc[3][0])), fadd(fadd(acc[0][1], acc[2][1]), fadd(acc[1][1], acc[3][1])),
+                             fadd(fadd(acc[0][2], acc[2][2]), fadd(acc[1][2], acc[3][2])), fadd(fadd(acc[0][3], acc[2][3]), fadd(acc[1][3], acc[3][3])));
+        dst[1] = make_float4(fadd(fadd(acc[0][4], acc[2][4]), fadd(acc[1][4], acc[3][4])), fadd(fadd(acc[0][5], acc[2][5]), fadd(acc[1][5], acc[3][5])),
+                             fadd(fadd(acc[0][6], acc[2][6]), fadd(acc[1][6], acc[3][6])), fadd(fadd(acc[0][7], acc[2][7]), fadd(acc[1][7], acc[3][7])));
+        named_bar_sync(1 + grp, 128);
+        if (live) {
+            const int c = gt;                                            // one channel per thread of the group
             float vv[8];
             #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const float p0 = partl[(0 * 8 + k) * 128 + c], p1 = partl[(1 * 8 + k) * 128 + c];
-                const float p2 = partl[(2 * 8 + k) * 128 + c], p3 = partl[(3 * 8 + k) * 128 + c];
-                vv[k] = fadd(fadd(p0, p2), fadd(p1, p3));
-            }
+            for (int k = 0; k < 8; k++) vv[k] = part_g[k * 128 + c];
             const float t0 = fadd(vv[0], vv[4]), t1 = fadd(vv[1], vv[5]), t2 = fadd(vv[2], vv[6]), t3 = fadd(vv[3], vv[7]);
             double sumf = (double) fadd(fadd(t0, t1), fadd(t2, t3));
             for (int t = npT; t < tcount; t++)
                 sumf += (double) fmul(h2f(((const uint16_t *)(KV + (size_t) t * kAttnRow))[c]), h2f(p_q[t]));
             const float ov = (float) sumf;
             a.out[(size_t) n * E + h * 128 + c] = ov;
-            // channels [32 w, 32 w + 32) of head h are Q8_0 block 4 h + w of the wo matmul's input
+            // channels [32 w, 32 w + 32) of head h are Q8_0 block 4 h + w of the wo matmul's input (w = warp within the group)
             if (a.aq_out) warp_quant_block(ov, lane, a.aq_out + (size_t) n * a.out_nbq * 32, a.da_out + (size_t) n * a.out_nbq * 4,
-                                           4 * h + warp, a.out_dscale);
+                                           4 * h + (gt >> 5), a.out_dscale);
         }
-        __syncthreads();
+        named_bar_sync(1 + grp, 128);
     }
 }
 
