@@ -96,6 +96,36 @@ sl.sync()
 if rank == 0:
     for i in range(24):
         ok = ok and bool((outs[i].view(np.uint32) == ref.forward(xs[i:i + 1]).view(np.uint32)).all())
+# throughput mode: ring = 2 steps for three sessions back to back, results collected later in issue order (b200_pipeline_collect);
+# a session's next token is issued only after its previous result is back -- same tokens as stepping the sessions one by one
+dist.barrier()
+lib.b200_pipeline_collect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+res = torch.zeros((3, sh.n_embd), dtype=torch.float32, device="cuda")
+sess = [1, 2, 3]
+xs3 = rng.standard_normal((4, 3, sh.n_embd), dtype=np.float32)            # 4 rounds x 3 sessions
+pipelined = np.zeros_like(xs3)
+window = world if transport == "peer" else 1                               # over NCCL a step is collected before the next is issued
+buf = torch.zeros((3, sh.n_embd), dtype=torch.float32, device="cuda")
+for rnd in range(4):
+    if rank == 0:
+        buf.copy_(torch.from_numpy(xs3[rnd]))
+        torch.cuda.synchronize()
+    issued = 0
+    for j in range(3 + window):
+        if j >= window and rank == 0:
+            capi.check(lib.b200_pipeline_collect(sl.handle, 1, C.c_void_p(res.data_ptr() + 4 * sh.n_embd * (j - window))))
+        if j < 3:
+            capi.check(lib.b200_pipeline_step_session(sl.handle, sess[j], C.c_void_p(buf.data_ptr() + 4 * sh.n_embd * j), 1, 2))
+    sl.sync()
+    if rank == 0:
+        torch.cuda.synchronize()
+        pipelined[rnd] = res.cpu().numpy()
+    dist.barrier()
+if rank == 0:
+    for rnd in range(4):
+        for j, k in enumerate(sess):
+            want = ref.session_forward(k, xs3[rnd, j:j + 1])[0]
+            ok = ok and bool((pipelined[rnd, j].view(np.uint32) == want.view(np.uint32)).all())
 dist.barrier()
 capi.check(lib.b200_pipeline_destroy(sl.handle))
 err = lib.b200_pipeline_error(sl.handle)

@@ -75,3 +75,66 @@ def test_two_rank_pipeline_matches_single_slice(tmp_path):
     for raw, n in zip(got, (9, 1, 1, 3)):
         x = rng.standard_normal((n, sh.n_embd), dtype=np.float32)
         assert whole.forward(x).tobytes() == raw
+
+
+def test_join_pipeline_falls_back_to_nccl_unless_every_rank_maps_its_neighbours(monkeypatch):
+    """Host logic of the transport choice (pipeline.join_pipeline) with a fake C ABI, one thread per rank over in-memory
+    collectives: the peer-memory mailboxes are used only if EVERY rank exported its handle, connected, and reports the peer
+    transport; one failing rank sends all of them to NCCL."""
+    import threading
+    import types
+
+    from distributedllm_b200 import capi, pipeline
+
+    def run(world, failing_rank, stage):
+        tls = threading.local()
+        calls = {r: [] for r in range(world)}
+
+        def fake_lib():
+            rank = tls.rank
+            L = types.SimpleNamespace()
+            L.b200_pipeline_unique_id = lambda p: 0
+            L.b200_pipeline_init = lambda h, r, w, p: calls[rank].append("init") or 0
+            L.b200_pipeline_mailbox_export = lambda h, p: (1 if (rank == failing_rank and stage == "export") else 0)
+            L.b200_pipeline_mailbox_connect = lambda h, p, w: (4 if (rank == failing_rank and stage == "connect") else 0)
+            L.b200_pipeline_transport = lambda h: 1
+            L.b200_pipeline_set_transport = lambda h, peer: calls[rank].append(("set", peer)) or 0
+            L.b200_last_error = lambda: b""
+            return L
+        monkeypatch.setattr(capi, "lib", fake_lib)
+        barrier = threading.Barrier(world)
+        slots = [None] * world
+        root = {}
+        results = {}
+
+        def worker(rank):
+            tls.rank = rank
+
+            def bcast(data, n):
+                if rank == 0:
+                    root["v"] = data
+                barrier.wait()
+                v = root["v"]
+                barrier.wait()
+                return v
+
+            def gather(data):
+                slots[rank] = data
+                barrier.wait()
+                out = list(slots)
+                barrier.wait()
+                return out
+            results[rank] = pipeline.join_pipeline(types.SimpleNamespace(handle=rank), rank, world, bcast, gather)
+        ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(30)
+        return results, calls
+
+    res, calls = run(4, failing_rank=-1, stage="")
+    assert set(res.values()) == {"peer"} and all(c[-1] == ("set", 1) for c in calls.values())
+    for stage in ("export", "connect"):
+        res, calls = run(4, failing_rank=2, stage=stage)
+        assert set(res.values()) == {"nccl"}, (stage, res)
+        assert all(c[-1] == ("set", 0) for c in calls.values())
