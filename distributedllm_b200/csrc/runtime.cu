@@ -1930,7 +1930,22 @@ int b200_extra_load(const char * path, int device, b200_extra_t ** out) {
     try { fp.reset(new GgjtFile(path, true)); }
     catch (const std::exception & ex) { return fail(B200_EFILE, "error loading extra layers: %s", ex.what()); }
     GgjtFile & f = *fp;
-    std::unique_ptr<b200_extra> e(new b200_extra());
+    // frees the stream and every device allocation if the load fails half-way (a node keeps running after a bad extra-layers file)
+    struct ExtraGuard {
+        b200_extra * p;
+        ~ExtraGuard() {
+            if (!p) return;
+            b200_slice * c = &p->ctx;
+            if (c->stream) cudaStreamSynchronize(c->stream);
+            for (void * q : c->allocs) cudaFree(q);
+            if (c->ev0) cudaEventDestroy(c->ev0);
+            if (c->ev1) cudaEventDestroy(c->ev1);
+            if (c->stream) cudaStreamDestroy(c->stream);
+            delete p;
+        }
+    };
+    ExtraGuard e_guard{new b200_extra()};
+    b200_extra * e = e_guard.p;
     b200_slice * s = &e->ctx;
     s->device = device; s->n_sm = prop.multiProcessorCount;
     s->use_pdl = false; s->use_graph = false;
@@ -1967,7 +1982,8 @@ int b200_extra_load(const char * path, int device, b200_extra_t ** out) {
     B200_CUDA(cudaEventCreate(&s->ev1));
     e->vocab = std::move(f.vocab);
     for (int i = 0; i < (int) e->vocab.size(); i++) e->token_to_id[e->vocab[i].first] = i;
-    *out = e.release();
+    *out = e;
+    e_guard.p = nullptr;
     return 0;
 }
 
