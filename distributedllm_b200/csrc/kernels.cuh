@@ -27,17 +27,21 @@ namespace b200 {
 //               as signed bytes, ready for dp4a
 //        64 B : fp16 d of row r, blocks 4q..4q+3 at 512 + 8*r
 // Q8_0 chunk (1088 B = 34 B/block): 512 B words w of 4 blocks per lane, 512 B words w+4, 64 B scales.
+// Q4_1 chunk (640 B = 20 B/block): the Q4_0 shape with the nibbles left UNSIGNED (0..15, no XOR) + 64 B of fp16 minima
+//       at 576 + 8*r.  ggml_vec_dot_q4_1_q8_1 (ggml.c:2700-2733): acc_l = fma(d0*d1, float(sum n*a), acc_l) with an
+//       f32 (unrounded) activation scale d1, plus a SCALAR chain summs += m * s (s = d1 * sum of the block's quants).
 // A warp reads a chunk with one conflict-free LDS.128 (+ one LDS.64) per lane.
 // =============================================================================================
-constexpr int kWT_F16 = 1, kWT_Q4_0 = 2, kWT_Q8_0 = 8;
-constexpr int kQ4Chunk = 576, kQ8Chunk = 1088;
+constexpr int kWT_F16 = 1, kWT_Q4_0 = 2, kWT_Q4_1 = 3, kWT_Q8_0 = 8;
+constexpr int kQ4Chunk = 576, kQ41Chunk = 640, kQ8Chunk = 1088;
 constexpr int kWPC = 4;                 // consumer warps per CTA (8 rows x G groups each)
 constexpr int kConsumers = kWPC * 32;
 constexpr int kQS = 4;                  // quads per ring stage (nbq is padded to a multiple of kQS at pack time)
 constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: int->float through the dp4a accumulator
 constexpr int kMagicI = 0x4B400000;
 
-__host__ __device__ constexpr int chunk_bytes(int wt) { return wt == kWT_Q4_0 ? kQ4Chunk : kQ8Chunk; }
+__host__ __device__ constexpr int chunk_bytes(int wt) { return wt == kWT_Q4_0 ? kQ4Chunk : (wt == kWT_Q4_1 ? kQ41Chunk : kQ8Chunk); }
+__host__ __device__ constexpr bool wt_nibbles(int wt) { return wt == kWT_Q4_0 || wt == kWT_Q4_1; }
 
 struct PackedW {
     const uint8_t * data;
@@ -68,25 +72,27 @@ __global__ void k_repack(RepackArgs a) {
         if (a.mode == 1)      { const int gps = a.rows_per_src / 8; s = gi / gps; sg = gi % gps; }
         else if (a.mode == 2) { s = gi & 1; sg = gi >> 1; }
         else                  { s = 0; sg = gi; }
-        const int bsz = a.wtype == kWT_Q4_0 ? 18 : 34;
+        const int bsz = a.wtype == kWT_Q4_0 ? 18 : (a.wtype == kWT_Q4_1 ? 20 : 34);
         uint32_t out = 0;
         const bool src_ok = s < 3 && a.src[s] != nullptr;
-        if (a.wtype == kWT_Q4_0) {
+        if (wt_nibbles(a.wtype)) {
+            const bool q41 = a.wtype == kWT_Q4_1;
             if (wi < 128) {                                  // nibble words
                 const int lane = wi >> 2, bq = wi & 3, r = lane >> 2, w = lane & 3;
                 const int row = sg * 8 + r, b = q * 4 + bq;
                 if (src_ok && row < a.rows_per_src && b < a.nb) {
                     const uint8_t * blk = a.src[s] + ((long long) row * a.nb + b) * bsz;
-                    const uint16_t * p = (const uint16_t *)(blk + 2 + 4 * w);
-                    out = ((uint32_t) p[0] | ((uint32_t) p[1] << 16)) ^ 0x88888888u;
+                    const uint16_t * p = (const uint16_t *)(blk + (q41 ? 4 : 2) + 4 * w);
+                    out = ((uint32_t) p[0] | ((uint32_t) p[1] << 16)) ^ (q41 ? 0u : 0x88888888u);
                 }
-            } else {                                         // scales: 16 words = 8 rows x 4 halves
-                const int h0 = (wi - 128) * 2;
+            } else {                                         // scales (then Q4_1 minima): 16 words = 8 rows x 4 halves
+                const int sel = (wi - 128) >> 4;             // 0: d at +0, 1: m at +2
+                const int h0 = ((wi - 128) & 15) * 2;
                 uint32_t v[2] = {0, 0};
                 for (int k = 0; k < 2; k++) {
                     const int r = (h0 + k) >> 2, bq = (h0 + k) & 3, row = sg * 8 + r, b = q * 4 + bq;
                     if (src_ok && row < a.rows_per_src && b < a.nb)
-                        v[k] = *(const uint16_t *)(a.src[s] + ((long long) row * a.nb + b) * bsz);
+                        v[k] = *(const uint16_t *)(a.src[s] + ((long long) row * a.nb + b) * bsz + 2 * sel);
                 }
                 out = v[0] | (v[1] << 16);
             }
@@ -190,6 +196,8 @@ struct GemvArgs {
     const float * x;      int ldx;       // PRO_PLAIN / PRO_NORM: input [N][ldx], K valid per row
     const float * norm_w;                // PRO_NORM: weight [K]
     const int * aq_in; const float * da_in;   // PRO_PREQ: pre-quantised input, [N][nbq*32] words + [N][nbq*4] scales
+    int in_soff, out_soff;               // Q4_1 weights (Q8_1 activations): the block sums s live in a second plane, this many
+                                         // floats behind the scales (da_in / da_out); 0 for Q8_0 activations
     const float * resid;  int ldr;       // EPI_RESID
     float * y;            int ldy;       // output [N][ldy]
     int * aq_out; float * da_out; int out_nbq; float out_dscale;   // EPI_GATEQ / EPI_RESID_NQ: quantised output for the next matmul
@@ -206,7 +214,7 @@ struct GemvArgs {
     uint2 * mb_peer_inbox; size_t mb_slot_elems;   // EPI_RESID_SEND: next rank's inbox (mapped peer memory), elements per slot
 };
 
-__host__ __device__ inline size_t act_bytes_per_col(int nbq) { return (size_t) nbq * (128 + 16); }
+__host__ __device__ inline size_t act_bytes_per_col(int nbq, int wt) { return (size_t) nbq * (128 + 16 + (wt == kWT_Q4_1 ? 16 : 0)); }
 
 
 // (double) of a NON-NEGATIVE float, bit-exact, on the integer pipes: F2F.F64.F32 runs on the quarter-rate XU pipe and
@@ -219,15 +227,24 @@ __device__ __forceinline__ double widen_nonneg(float f) {
 // rint() of |x| <= 2^22 through the FMA pipe (round-half-even, as F2I.RN / _mm256_round_ps(NEAREST)) instead of XU
 __device__ __forceinline__ int rint_small(float x) { return __float_as_int(fadd(x, kMagic)) - kMagicI; }
 
+// unsigned bytes x signed bytes (Q4_1's nibbles are 0..15: `(x<<4)&0xF0` is 16*nibble as an UNSIGNED byte)
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+    int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
 // Q8_0 act-quant (ggml.c:1215-1252) of the 32 values held one per lane, written straight into the
 // dp4a word layout the matmul consumers read: words [Q][w&3][bq][w>>2], scale [b] (x dscale).
-__device__ __forceinline__ void warp_quant_block(float v, int lane, int * aq_col, float * da_col, int b, float dscale) {
+// soff != 0: Q8_1 instead (quantize_row_q8_1, ggml.c:1426-1472): the scale is NOT rounded to fp16 and
+// s = d * (sum of the quants) is stored soff floats behind the scale.
+__device__ __forceinline__ void warp_quant_block(float v, int lane, int * aq_col, float * da_col, int b, float dscale, int soff = 0) {
     float amax = fabsf(v);
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
+    const float dq = __fdiv_rn(amax, 127.f);
+    const float d = soff ? dq : h2f(f2h(dq));
     const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
-    uint32_t pk = ((uint32_t)(rint_small(fmul(v, id)) & 0xFF)) << (8 * (lane & 3));
+    const int qv = rint_small(fmul(v, id));
+    uint32_t pk = ((uint32_t)(qv & 0xFF)) << (8 * (lane & 3));
     pk |= __shfl_xor_sync(0xffffffffu, pk, 1);
     pk |= __shfl_xor_sync(0xffffffffu, pk, 2);
     if ((lane & 3) == 0) {
@@ -235,43 +252,59 @@ __device__ __forceinline__ void warp_quant_block(float v, int lane, int * aq_col
         aq_col[(b >> 2) * 32 + (w & 3) * 8 + (b & 3) * 2 + (w >> 2)] = (int) pk;
     }
     if (lane == 0) da_col[b] = fmul(d, dscale);
+    if (soff) {
+        int qs = qv;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+        if (lane == 0) da_col[soff + b] = fmul(d, (float) qs);
+    }
 }
 
 // quantise one 32-float block held in registers by ONE thread into shared memory
 // `rot`: v[4*w8 .. 4*w8+3] holds 16-byte chunk (w8 + rot) & 7 of the block (bank-conflict-free rotated smem reads)
+// WT == Q4_1: Q8_1 (f32 scale, block sum s into sn[b]); otherwise Q8_0.
 template <int WT>
-__device__ __forceinline__ void thread_quant_block(const float (&v)[32], int * an, float * dn, int b, int rot = 0) {
+__device__ __forceinline__ void thread_quant_block(const float (&v)[32], int * an, float * dn, int b, int rot = 0, float * sn = nullptr) {
     float m[8];
     #pragma unroll
     for (int j = 0; j < 8; j++) m[j] = fmaxf(fmaxf(fabsf(v[j]), fabsf(v[j + 8])), fmaxf(fabsf(v[j + 16]), fabsf(v[j + 24])));
     const float amax = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-    const float d = h2f(f2h(__fdiv_rn(amax, 127.f)));
+    const float dq = __fdiv_rn(amax, 127.f);
+    const float d = (WT == kWT_Q4_1) ? dq : h2f(f2h(dq));
     const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
-    dn[b] = (WT == kWT_Q4_0) ? fmul(d, 0.0625f) : d;        // the 1/16 of the nibble placement, folded (exact)
+    dn[b] = wt_nibbles(WT) ? fmul(d, 0.0625f) : d;          // the 1/16 of the nibble placement, folded (exact)
     int * dst = an + (b >> 2) * 32 + (b & 3) * 2;
+    int qsum = 0;
     #pragma unroll
     for (int w = 0; w < 8; w++) {
         uint32_t pk = 0;
         #pragma unroll
-        for (int j = 0; j < 4; j++) pk |= ((uint32_t)(rint_small(fmul(v[w*4 + j], id)) & 0xFF)) << (8 * j);
+        for (int j = 0; j < 4; j++) {
+            const int qv = rint_small(fmul(v[w*4 + j], id));
+            if (WT == kWT_Q4_1) qsum += qv;
+            pk |= ((uint32_t)(qv & 0xFF)) << (8 * j);
+        }
         const int ww = (w + rot) & 7;
         dst[(ww & 3) * 8 + (ww >> 2)] = (int) pk;
     }
+    if (WT == kWT_Q4_1) sn[b] = fmul(d, (float) qsum);
 }
 
 template <int WT, int G, int NC, int PRO, int EPI, bool RING>
 __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
-    constexpr int CB = (WT == kWT_Q4_0) ? kQ4Chunk : kQ8Chunk;
+    constexpr int CB = chunk_bytes(WT);
+    constexpr bool Q41 = WT == kWT_Q4_1;
     constexpr int TR = kWPC * G;
     extern __shared__ __align__(128) uint8_t smem[];
     const int nbq = a.W.nbq, K = a.W.K, nb = a.W.nb;
     const int NS = a.NS;
     constexpr int stage_bytes = kQS * TR * CB;
-    // smem: [ring NS*stage][act words NC*nbq*128][act scales NC*nbq*16][full 16][empty 16][act bar][red 4][gq NC*32]
+    // smem: [ring NS*stage][act words NC*nbq*128][act scales NC*nbq*16][Q4_1: act block sums NC*nbq*16][full 16][empty 16][act bar][red 4][gq NC*32]
     uint8_t * ring = smem;
     int * a_s = (int *)(smem + (RING ? (size_t) NS * stage_bytes : 0));
     float * da_s = (float *)((uint8_t *) a_s + (size_t) NC * nbq * 128);
-    uint64_t * full = (uint64_t *)((uint8_t *) da_s + (size_t) NC * nbq * 16);
+    float * sa_s = da_s + (size_t) NC * nbq * 4;                         // Q4_1 only
+    uint64_t * full = (uint64_t *)((uint8_t *) da_s + (size_t) NC * nbq * (Q41 ? 32 : 16));
     uint64_t * empty = full + 16;
     uint64_t * actbar = empty + 16;
     double * red = (double *)(actbar + 2);           // [kWPC]
@@ -344,23 +377,25 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
         // the producer of the activation already quantised it (attention / gate epilogue): two bulk copies
         if (tid == 0) {
             const uint32_t b1 = (uint32_t) ncols * nbq * 128, b2 = (uint32_t) ncols * nbq * 16;
-            mbar_arrive_expect_tx(actbar, b1 + b2);
+            mbar_arrive_expect_tx(actbar, b1 + b2 + (Q41 ? b2 : 0u));
             bulk_g2s(a_s, a.aq_in + (size_t) col0 * nbq * 32, b1, actbar);
             bulk_g2s(da_s, a.da_in + (size_t) col0 * nbq * 4, b2, actbar);
+            if (Q41) bulk_g2s(sa_s, a.da_in + a.in_soff + (size_t) col0 * nbq * 4, b2, actbar);
         }
         if (RING && lane == 0) mbar_arrive(actbar + 1);
         for (int n = ncols; n < NC; n++) {
             for (int i = tid; i < nbq * 32; i += kConsumers) a_s[(size_t) n * nbq * 32 + i] = 0;
-            for (int i = tid; i < nbq * 4; i += kConsumers) da_s[(size_t) n * nbq * 4 + i] = 0.f;
+            for (int i = tid; i < nbq * 4; i += kConsumers) { da_s[(size_t) n * nbq * 4 + i] = 0.f; if (Q41) sa_s[(size_t) n * nbq * 4 + i] = 0.f; }
         }
         mbar_wait(actbar, 0);
     } else {
         for (int n = 0; n < NC; n++) {
             int * an = a_s + (size_t) n * nbq * 32;
             float * dn = da_s + (size_t) n * nbq * 4;
+            float * sn = sa_s + (size_t) n * nbq * 4;
             if (n >= ncols) {                              // padded column: zeros
                 for (int i = tid; i < nbq * 32; i += kConsumers) an[i] = 0;
-                for (int i = tid; i < nbq * 4; i += kConsumers) dn[i] = 0.f;
+                for (int i = tid; i < nbq * 4; i += kConsumers) { dn[i] = 0.f; if (Q41) sn[i] = 0.f; }
                 continue;
             }
             const float * x = a.x + (size_t)(col0 + n) * a.ldx;
@@ -368,6 +403,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 int * dst = an + (b >> 2) * 32 + (b & 3) * 2;
                 for (int w = 0; w < 4; w++) { dst[w * 8] = 0; dst[w * 8 + 1] = 0; }
                 dn[b] = 0.f;
+                if (Q41) sn[b] = 0.f;
             }
             if (PRO == PRO_NORM && nb <= kConsumers) {
                 // one global round trip: x block and norm weights in flight together, x kept in registers
@@ -410,7 +446,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 if (own) {
                     #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmul(fmul(v[j], scale), wn[j]);
-                    thread_quant_block<WT>(v, an, dn, tid, rot);
+                    thread_quant_block<WT>(v, an, dn, tid, rot, sn);
                 }
             } else {
                 float scale = 1.0f;
@@ -440,7 +476,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                         }
                         v[j*4] = t.x; v[j*4+1] = t.y; v[j*4+2] = t.z; v[j*4+3] = t.w;
                     }
-                    thread_quant_block<WT>(v, an, dn, b);
+                    thread_quant_block<WT>(v, an, dn, b, 0, sn);
                 }
             }
         }
@@ -462,10 +498,11 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
     }
     for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
         float acc[G][NC][2];
+        float summ[G][NC];                  // Q4_1: the scalar chain summs += m * s of row r (every w-thread of the row keeps a copy)
         #pragma unroll
         for (int g = 0; g < G; g++)
             #pragma unroll
-            for (int n = 0; n < NC; n++) { acc[g][n][0] = 0.f; acc[g][n][1] = 0.f; }
+            for (int n = 0; n < NC; n++) { acc[g][n][0] = 0.f; acc[g][n][1] = 0.f; summ[g][n] = 0.f; }
         const uint8_t * gsrc = a.W.data + (long long) tile * a.W.tile_bytes;
 
         for (int s = 0; s < n_stage; s++) {
@@ -481,13 +518,14 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
             #pragma unroll
             for (int qi = 0; qi < kQS; qi++) {
                 const int Q = s * kQS + qi;
-                uint4 wv[G], wv2[G]; uint2 sc[G];
+                uint4 wv[G], wv2[G]; uint2 sc[G], mc[G];
                 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const uint8_t * ch = base + (size_t)(qi * TR + g) * CB;
                     wv[g] = *(const uint4 *)(ch + lane * 16);
                     if (WT == kWT_Q8_0) { wv2[g] = *(const uint4 *)(ch + 512 + lane * 16); sc[g] = *(const uint2 *)(ch + 1024 + r * 8); }
                     else sc[g] = *(const uint2 *)(ch + 512 + r * 8);
+                    mc[g] = Q41 ? *(const uint2 *)(ch + 576 + r * 8) : make_uint2(0u, 0u);
                 }
                 #pragma unroll
                 for (int n = 0; n < NC; n++) {
@@ -497,20 +535,33 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                     const int alo[4] = {a01.x, a01.z, a23.x, a23.z};
                     const int ahi[4] = {a01.y, a01.w, a23.y, a23.w};
                     const float da[4] = {dav.x, dav.y, dav.z, dav.w};
+                    float sa[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (Q41) { const float4 sav = *(const float4 *)(sa_s + (size_t) n * nbq * 4 + Q * 4); sa[0] = sav.x; sa[1] = sav.y; sa[2] = sav.z; sa[3] = sav.w; }
                     #pragma unroll
                     for (int g = 0; g < G; g++) {
                         const uint32_t ww[4] = {wv[g].x, wv[g].y, wv[g].z, wv[g].w};
                         const uint32_t ww2[4] = {wv2[g].x, wv2[g].y, wv2[g].z, wv2[g].w};
                         const uint32_t sw[2] = {sc[g].x, sc[g].y};
+                        const uint32_t mw[2] = {mc[g].x, mc[g].y};
                         #pragma unroll
                         for (int bq = 0; bq < 4; bq++) {
                             const uint16_t dh = (uint16_t)(sw[bq >> 1] >> (16 * (bq & 1)));
                             const float D = fmul(h2f(dh), da[bq]);
-                            int lo, hi;
-                            if (WT == kWT_Q4_0) { lo = (int)((ww[bq] << 4) & 0xF0F0F0F0u); hi = (int)(ww[bq] & 0xF0F0F0F0u); }
-                            else                { lo = (int) ww[bq]; hi = (int) ww2[bq]; }
-                            const float f0 = fadd(__int_as_float(__dp4a(lo, alo[bq], kMagicI)), -kMagic);
-                            const float f1 = fadd(__int_as_float(__dp4a(hi, ahi[bq], kMagicI)), -kMagic);
+                            float f0, f1;
+                            if (Q41) {
+                                // summs += fp16->f32(m) * s first (ggml.c:2712), then the lane fma: two independent chains
+                                const uint16_t mh = (uint16_t)(mw[bq >> 1] >> (16 * (bq & 1)));
+                                summ[g][n] = fadd(summ[g][n], fmul(h2f(mh), sa[bq]));
+                                const uint32_t lo = (ww[bq] << 4) & 0xF0F0F0F0u, hi = ww[bq] & 0xF0F0F0F0u;
+                                f0 = fadd(__int_as_float(dp4a_us(lo, alo[bq], kMagicI)), -kMagic);
+                                f1 = fadd(__int_as_float(dp4a_us(hi, ahi[bq], kMagicI)), -kMagic);
+                            } else {
+                                int lo, hi;
+                                if (WT == kWT_Q4_0) { lo = (int)((ww[bq] << 4) & 0xF0F0F0F0u); hi = (int)(ww[bq] & 0xF0F0F0F0u); }
+                                else                { lo = (int) ww[bq]; hi = (int) ww2[bq]; }
+                                f0 = fadd(__int_as_float(__dp4a(lo, alo[bq], kMagicI)), -kMagic);
+                                f1 = fadd(__int_as_float(__dp4a(hi, ahi[bq], kMagicI)), -kMagic);
+                            }
                             acc[g][n][0] = ffma(D, f0, acc[g][n][0]);
                             acc[g][n][1] = ffma(D, f1, acc[g][n][1]);
                         }
@@ -533,7 +584,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 float t = fadd(acc[g][n][0], acc[g][n][1]);
                 t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 2));
                 t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 1));
-                res[g][n] = t;
+                res[g][n] = Q41 ? fadd(t, summ[g][n]) : t;          // hsum_float_8(acc) + summs
             }
         if (EPI == EPI_GATE || EPI == EPI_GATEQ) {
             const int row = (tile * kWPC + warp) * 8 + r;
@@ -550,7 +601,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 named_bar_sync(1, kConsumers);
                 for (int n = warp; n < ncols; n += kWPC)
                     warp_quant_block(gq[n * 32 + lane], lane, a.aq_out + (size_t)(col0 + n) * a.out_nbq * 32,
-                                     a.da_out + (size_t)(col0 + n) * a.out_nbq * 4, tile, a.out_dscale);
+                                     a.da_out + (size_t)(col0 + n) * a.out_nbq * 4, tile, a.out_dscale, a.out_soff);
                 named_bar_sync(1, kConsumers);
             }
         } else if (w == 0) {
@@ -610,7 +661,7 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
                 const float val = gq[n * 32 + lane];
                 const float wv = row < a.out_rows ? a.nq_norm_w[row] : 0.f;
                 warp_quant_block(fmul(fmul(val, scale), wv), lane, a.aq_out + (size_t)(col0 + n) * a.out_nbq * 32,
-                                 a.da_out + (size_t)(col0 + n) * a.out_nbq * 4, tile, a.out_dscale);
+                                 a.da_out + (size_t)(col0 + n) * a.out_nbq * 4, tile, a.out_dscale, a.out_soff);
             }
             if (lane == 0) {                                   // the last CTA through re-arms the counters
                 if (atomicAdd(cnt + 1, 1) == nt - 1) { cnt[0] = 0; cnt[1] = 0; }
@@ -629,7 +680,8 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
 // =============================================================================================
 struct NormQuantArgs {
     const float * x; int ldx; const float * norm_w; int K;
-    int * aq; float * da; int nbq;            // [N][nbq*32] words, [N][nbq*4] scales (x 1/16 for Q4_0 weights)
+    int * aq; float * da; int nbq;            // [N][nbq*32] words, [N][nbq*4] scales (x 1/16 for Q4_0 / Q4_1 weights)
+    int soff;                                 // Q4_1: block sums s at da + soff
 };
 
 template <int WT>
@@ -666,7 +718,7 @@ __global__ void __launch_bounds__(256) k_norm_quant(const NormQuantArgs a) {
             v[j*4]   = fmul(fmul(t.x, scale), wv.x); v[j*4+1] = fmul(fmul(t.y, scale), wv.y);
             v[j*4+2] = fmul(fmul(t.z, scale), wv.z); v[j*4+3] = fmul(fmul(t.w, scale), wv.w);
         }
-        thread_quant_block<WT>(v, an, dn, b);
+        thread_quant_block<WT>(v, an, dn, b, 0, dn + a.soff);
     }
 }
 
@@ -1083,6 +1135,7 @@ struct Attn128Args {
     const float2 * cs; const uint16_t * texp;
     float * out;                  // [N][E]
     int * aq_out; float * da_out; int out_nbq; float out_dscale;   // optional: Q8_0-quantised output for the wo matmul
+    int out_soff;                                                    // Q4_1 weights: Q8_1 instead, block sums at da_out + out_soff
     int n_ctx; float kq_scale;
     unsigned long long * trace;
     const int2 * cols; size_t sess_stride;   // batched step (FUSE only): column n = (session, position); each column is an N = 1 step
@@ -1349,7 +1402,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_attn128(const
         a.out[(size_t) n * E + h * 128 + c] = ov;
         // channels [32g, 32g+32) of head h are Q8_0 block 4h+g of the wo matmul's input: quantise here
         if (a.aq_out) warp_quant_block(ov, lane, a.aq_out + (size_t) n * a.out_nbq * 32, a.da_out + (size_t) n * a.out_nbq * 4,
-                                       4 * h + g, a.out_dscale);
+                                       4 * h + g, a.out_dscale, a.out_soff);
     }
     if (threadIdx.x == 0) B200_TRACE(a.trace, 3);
 }
@@ -1430,7 +1483,7 @@ struct AttnTiledArgs {
     const int * n_past; int E, H, N;
     const uint16_t * texp;
     float * out;                                   // [N][E]
-    int * aq_out; float * da_out; int out_nbq; float out_dscale;
+    int * aq_out; float * da_out; int out_nbq; float out_dscale; int out_soff;
     float kq_scale;
     int t_rows, t_pad;                             // staged rows (>= n_past + N) and the padded score row length
 };
@@ -1581,7 +1634,7 @@ __global__ void __launch_bounds__(512) k_attn128_tiled(const AttnTiledArgs a) {
             a.out[(size_t) n * E + h * 128 + c] = ov;
             // channels [32 w, 32 w + 32) of head h are Q8_0 block 4 h + w of the wo matmul's input (w = warp within the group)
             if (a.aq_out) warp_quant_block(ov, lane, a.aq_out + (size_t) n * a.out_nbq * 32, a.da_out + (size_t) n * a.out_nbq * 4,
-                                           4 * h + (gt >> 5), a.out_dscale);
+                                           4 * h + (gt >> 5), a.out_dscale, a.out_soff);
         }
         named_bar_sync(1 + grp, 128);
     }

@@ -61,6 +61,7 @@ struct b200_slice {
     float2 * cs = nullptr; uint16_t * texp = nullptr, * tsilu = nullptr;
     int * aq_att = nullptr, * aq_gate = nullptr; float * da_att = nullptr, * da_gate = nullptr;   // pre-quantised activations
     int nbqE = 0, nbqF = 0;
+    int soffE = 0, soffF = 0;              // Q4_1 slices (Q8_1 activations): floats between the scale plane and the block-sum plane of da_*
     int * aq_x = nullptr; float * da_x = nullptr; int * nq_counter = nullptr; double * nq_partial = nullptr;   // normalised+quantised layer input (last-CTA epilogue)
     std::map<GraphKey, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
@@ -122,12 +123,12 @@ static void prof_end(b200_slice * s) {
 // ---------------------------------------------------------------- kernel dispatch
 template <int WT, int G, int NC, int PRO, int EPI, bool RING>
 static int launch_gemv_t(b200_slice * s, GemvArgs a) {
-    constexpr int CB = (WT == kWT_Q4_0) ? kQ4Chunk : kQ8Chunk;
+    constexpr int CB = chunk_bytes(WT);
     constexpr int TR = kWPC * G;
     auto kern = k_gemv<WT, G, NC, PRO, EPI, RING>;
     static bool attr_set[16] = {false};
     const size_t stage = (size_t) kQS * TR * CB;
-    const size_t act = (size_t) NC * act_bytes_per_col(a.W.nbq) + 34 * 8 + kWPC * 8 + (size_t) NC * 128 + 64 +
+    const size_t act = (size_t) NC * act_bytes_per_col(a.W.nbq, WT) + 34 * 8 + kWPC * 8 + (size_t) NC * 128 + 64 +
                        ((NC == 1 && PRO == PRO_NORM) ? (size_t) a.W.K * 4 : 0);
     // Ring depth: as deep as possible while EVERY tile of the matrix still gets a co-resident CTA (no second wave):
     // wide matrices (qkv 384 tiles, w1|w3 688) run 3-5 small-ring CTAs per SM, narrow ones (wo, w2: 128 tiles) one
@@ -197,6 +198,7 @@ static int launch_gemv_nc(b200_slice * s, const GemvArgs & a) {
 template <int G, int PRO, int EPI>
 static int launch_gemv(b200_slice * s, const GemvArgs & a) {
     if (a.W.wtype == kWT_Q4_0) return launch_gemv_nc<kWT_Q4_0, G, PRO, EPI>(s, a);
+    if (a.W.wtype == kWT_Q4_1) return launch_gemv_nc<kWT_Q4_1, G, PRO, EPI>(s, a);
     return launch_gemv_nc<kWT_Q8_0, G, PRO, EPI>(s, a);
 }
 
@@ -261,8 +263,9 @@ static int launch_f16(b200_slice * s, GemvF16Args a) {
 }
 
 static int launch_norm_quant(b200_slice * s, const float * x, int ldx, const float * norm_w, int N) {
-    NormQuantArgs q{x, ldx, norm_w, s->E, s->aq_x, s->da_x, s->nbqE};
+    NormQuantArgs q{x, ldx, norm_w, s->E, s->aq_x, s->da_x, s->nbqE, s->soffE};
     if (s->wtype == kWT_Q4_0) return launch_simple(s, k_norm_quant<kWT_Q4_0>, dim3(N, 1, 1), dim3(256, 1, 1), 0, q);
+    if (s->wtype == kWT_Q4_1) return launch_simple(s, k_norm_quant<kWT_Q4_1>, dim3(N, 1, 1), dim3(256, 1, 1), 0, q);
     return launch_simple(s, k_norm_quant<kWT_Q8_0>, dim3(N, 1, 1), dim3(256, 1, 1), 0, q);
 }
 
@@ -467,7 +470,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             if ((rc = launch_fast_any<FG_STORE>(s, Lw.qkv, nullptr, 0, s->qkv, 3 * E, N, 3 * E))) return rc;
         } else {
             GemvArgs g{}; g.W = Lw.qkv; g.x = cur; g.ldx = E; g.norm_w = Lw.attn_norm; g.y = s->qkv; g.ldy = 3 * E;
-            g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x;
+            g.N = N; g.out_rows = 3 * E; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x; g.in_soff = s->soffE;
             // layers after the first get their input already normalised + quantised by the previous w2's last CTA
             if (il > 0 && nq) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_STORE>(s, g))) return rc; }
             else if (N > 1) {
@@ -495,8 +498,8 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             aa.cs = s->cs; aa.texp = s->texp; aa.out = s->att;
             aa.n_ctx = s->n_ctx; aa.kq_scale = 1.0f / sqrtf((float) E / (float) H);
             const bool preq = s->wtype != kWT_F16;
-            const float dsc = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
-            if (preq) { aa.aq_out = s->aq_att; aa.da_out = s->da_att; aa.out_nbq = s->nbqE; aa.out_dscale = dsc; }
+            const float dsc = wt_nibbles(s->wtype) ? 0.0625f : 1.0f;
+            if (preq) { aa.aq_out = s->aq_att; aa.da_out = s->da_att; aa.out_nbq = s->nbqE; aa.out_dscale = dsc; aa.out_soff = s->soffE; }
             if (s->cols) {
                 // every column is an independent N = 1 step: the fused (RoPE + append) kernel, one cluster row per column
                 s->cur_class = 2;
@@ -520,7 +523,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
                 const int Tn = s->past[s->cur] + N;
                 AttnTiledArgs ta{};
                 ta.q16 = s->q16; ta.kc = kc; ta.vc = vc; ta.n_past = d_npast; ta.E = E; ta.H = H; ta.N = N; ta.texp = s->texp; ta.out = s->att;
-                if (preq) { ta.aq_out = s->aq_att; ta.da_out = s->da_att; ta.out_nbq = s->nbqE; ta.out_dscale = dsc; }
+                if (preq) { ta.aq_out = s->aq_att; ta.da_out = s->da_att; ta.out_nbq = s->nbqE; ta.out_dscale = dsc; ta.out_soff = s->soffE; }
                 ta.kq_scale = aa.kq_scale; ta.t_rows = Tn; ta.t_pad = (Tn + 31) & ~31;
                 const size_t tsm = (size_t) ta.t_rows * kAttnRow + (size_t) kAttnQB * ta.t_pad * 6 + 4 * 8 * 128 * 4 + kAttnQB * 256 + 64;
                 static bool tattr[16] = {false};
@@ -573,10 +576,10 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             if ((rc = launch_prep<false>(s, s->gate, FF, nullptr, FF, N))) return rc;
             if ((rc = launch_fast_any<FG_RESID>(s, Lw.w2, s->ffin, E, nxt, E, N, E))) return rc;
         } else {
-            const float dsc = s->wtype == kWT_Q4_0 ? 0.0625f : 1.0f;
+            const float dsc = wt_nibbles(s->wtype) ? 0.0625f : 1.0f;
             s->cur_class = 3;
             GemvArgs o{}; o.W = Lw.wo; o.x = s->att; o.ldx = E; o.resid = cur; o.ldr = E; o.y = s->ffin; o.ldy = E;
-            o.N = N; o.out_rows = E; o.tsilu = s->tsilu; o.aq_in = s->aq_att; o.da_in = s->da_att;
+            o.N = N; o.out_rows = E; o.tsilu = s->tsilu; o.aq_in = s->aq_att; o.da_in = s->da_att; o.in_soff = s->soffE; o.out_soff = s->soffE;
             o.nq_norm_w = Lw.ffn_norm; o.nq_counter = s->nq_counter; o.nq_partial = s->nq_partial; o.aq_out = s->aq_x; o.da_out = s->da_x; o.out_nbq = s->nbqE; o.out_dscale = dsc;
             if (D == 128) {
                 if (nq) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID_NQ>(s, o))) return rc; }
@@ -587,7 +590,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             }
             s->cur_class = 4;
             GemvArgs g{}; g.W = Lw.w13; g.x = s->ffin; g.ldx = E; g.norm_w = Lw.ffn_norm; g.y = s->gate; g.ldy = FF;
-            g.N = N; g.out_rows = FF; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x;
+            g.N = N; g.out_rows = FF; g.tsilu = s->tsilu; g.aq_in = s->aq_x; g.da_in = s->da_x; g.in_soff = s->soffE; g.out_soff = s->soffF;
             g.aq_out = s->aq_gate; g.da_out = s->da_gate; g.out_nbq = s->nbqF; g.out_dscale = dsc;
             if (nq) { if ((rc = launch_gemv<2, PRO_PREQ, EPI_GATEQ>(s, g))) return rc; }
             else if (N > 1) {
@@ -597,7 +600,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             else    { if ((rc = launch_gemv<2, PRO_NORM, EPI_GATEQ>(s, g))) return rc; }
             s->cur_class = 5;
             GemvArgs w{}; w.W = Lw.w2; w.resid = s->ffin; w.ldr = E; w.y = nxt; w.ldy = E;
-            w.N = N; w.out_rows = E; w.tsilu = s->tsilu; w.aq_in = s->aq_gate; w.da_in = s->da_gate;
+            w.N = N; w.out_rows = E; w.tsilu = s->tsilu; w.aq_in = s->aq_gate; w.da_in = s->da_gate; w.in_soff = s->soffF; w.out_soff = s->soffE;
             if (il + 1 < s->L && nq) {
                 w.nq_norm_w = s->layers[il + 1].attn_norm; w.nq_counter = s->nq_counter; w.nq_partial = s->nq_partial; w.aq_out = s->aq_x; w.da_out = s->da_x;
                 w.out_nbq = s->nbqE; w.out_dscale = dsc;
@@ -605,8 +608,9 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             } else if (s->fold_send && il == s->L - 1) {
                 w.mb_mine = (MailboxHdr *) s->mb_block;
                 w.mb_peer_inbox = (uint2 *)(s->mb_next + sizeof(MailboxHdr)); w.mb_slot_elems = s->mb_slot_floats;
-                if (s->wtype == kWT_Q4_0) rc = launch_gemv_t<kWT_Q4_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
-                else                      rc = launch_gemv_t<kWT_Q8_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
+                if (s->wtype == kWT_Q4_0)      rc = launch_gemv_t<kWT_Q4_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
+                else if (s->wtype == kWT_Q4_1) rc = launch_gemv_t<kWT_Q4_1, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
+                else                           rc = launch_gemv_t<kWT_Q8_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
                 if (rc) return rc;
             } else if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, w))) return rc;
         }
@@ -971,8 +975,8 @@ static int load_locked(b200_slice * s, const char * path) {
     try {
         const std::string p0 = "layers." + std::to_string(s->first_layer);
         s->wtype = (int) f.get(p0 + ".attention.wq.weight", {E, E}).type;
-        if (s->wtype != kWT_Q4_0 && s->wtype != kWT_Q8_0 && s->wtype != kWT_F16)
-            return fail(B200_EFILE, "weight type %d unsupported (Q4_0, Q8_0, F16)", s->wtype);
+        if (s->wtype != kWT_Q4_0 && s->wtype != kWT_Q4_1 && s->wtype != kWT_Q8_0 && s->wtype != kWT_F16)
+            return fail(B200_EFILE, "weight type %d unsupported (Q4_0, Q4_1, Q8_0, F16)", s->wtype);
         float * d_norms = nullptr;
         if ((rc = dev_alloc(s, &d_norms, (size_t) s->L * 2 * E))) return rc;
         norms.resize((size_t) s->L * 2 * E);
@@ -1035,16 +1039,19 @@ static int load_locked(b200_slice * s, const char * path) {
     if (s->wtype != kWT_F16) {
         s->nbqE = s->layers[0].wo.nbq; s->nbqF = s->layers[0].w2.nbq;
         const size_t nq = (size_t) s->n_ctx;
-        if ((rc = dev_alloc(s, &s->aq_att, nq * s->nbqE * 32)) || (rc = dev_alloc(s, &s->da_att, nq * s->nbqE * 4)) ||
-            (rc = dev_alloc(s, &s->aq_gate, nq * s->nbqF * 32)) || (rc = dev_alloc(s, &s->da_gate, nq * s->nbqF * 4))) return rc;
-        if ((rc = dev_alloc(s, &s->aq_x, nq * s->nbqE * 32)) || (rc = dev_alloc(s, &s->da_x, nq * s->nbqE * 4)) ||
+        // Q4_1: every scale array carries a second plane (Q8_1's block sums s) right behind the scales
+        const size_t pl = s->wtype == kWT_Q4_1 ? 2 : 1;
+        if (pl == 2) { s->soffE = (int)(nq * s->nbqE * 4); s->soffF = (int)(nq * s->nbqF * 4); }
+        if ((rc = dev_alloc(s, &s->aq_att, nq * s->nbqE * 32)) || (rc = dev_alloc(s, &s->da_att, pl * nq * s->nbqE * 4)) ||
+            (rc = dev_alloc(s, &s->aq_gate, nq * s->nbqF * 32)) || (rc = dev_alloc(s, &s->da_gate, pl * nq * s->nbqF * 4))) return rc;
+        if ((rc = dev_alloc(s, &s->aq_x, nq * s->nbqE * 32)) || (rc = dev_alloc(s, &s->da_x, pl * nq * s->nbqE * 4)) ||
             (rc = dev_alloc(s, &s->nq_counter, 2 * nq)) || (rc = dev_alloc(s, &s->nq_partial, nq * 256))) return rc;
         if ((rc = dev_alloc(s, &s->p_cnt, (size_t) s->L * kPPhases + 32))) return rc;
         B200_CUDA(cudaMemset(s->p_cnt, 0, ((size_t) s->L * kPPhases + 32) * 4));
-        B200_CUDA(cudaMemset(s->aq_x, 0, nq * s->nbqE * 128)); B200_CUDA(cudaMemset(s->da_x, 0, nq * s->nbqE * 16));
+        B200_CUDA(cudaMemset(s->aq_x, 0, nq * s->nbqE * 128)); B200_CUDA(cudaMemset(s->da_x, 0, pl * nq * s->nbqE * 16));
         B200_CUDA(cudaMemset(s->nq_counter, 0, 2 * nq * 4));
-        B200_CUDA(cudaMemset(s->aq_att, 0, nq * s->nbqE * 128));  B200_CUDA(cudaMemset(s->da_att, 0, nq * s->nbqE * 16));
-        B200_CUDA(cudaMemset(s->aq_gate, 0, nq * s->nbqF * 128)); B200_CUDA(cudaMemset(s->da_gate, 0, nq * s->nbqF * 16));
+        B200_CUDA(cudaMemset(s->aq_att, 0, nq * s->nbqE * 128));  B200_CUDA(cudaMemset(s->da_att, 0, pl * nq * s->nbqE * 16));
+        B200_CUDA(cudaMemset(s->aq_gate, 0, nq * s->nbqF * 128)); B200_CUDA(cudaMemset(s->da_gate, 0, pl * nq * s->nbqF * 16));
     }
     B200_CUDA(cudaMemset(s->kc, 0, s->n_sessions * s->sess_stride * 2));
     B200_CUDA(cudaMemset(s->vc, 0, s->n_sessions * s->sess_stride * 2));
@@ -1820,6 +1827,11 @@ __global__ void k_embed_rows(const uint8_t * emb, int type, int E, const int32_t
             const float d = h2f(*(const uint16_t *) blk);
             const int j = i & 31, q = blk[2 + (j & 15)];
             v = fmul((float)((j < 16 ? (q & 0x0F) : (q >> 4)) - 8), d);
+        } else if (type == kWT_Q4_1) {               // dequantize_row_q4_1, ggml.c:1543-1562: nibble * d, then + m (two roundings)
+            const uint8_t * blk = emb + ((size_t) t * (E / 32) + i / 32) * 20;
+            const float d = h2f(*(const uint16_t *) blk), m = h2f(*(const uint16_t *)(blk + 2));
+            const int j = i & 31, q = blk[4 + (j & 15)];
+            v = fadd(fmul((float)(j < 16 ? (q & 0x0F) : (q >> 4)), d), m);
         } else if (type == kWT_Q8_0) {
             const uint8_t * blk = emb + ((size_t) t * (E / 32) + i / 32) * 34;
             v = fmul((float)((const int8_t *)(blk + 2))[i & 31], h2f(*(const uint16_t *) blk));
@@ -1958,10 +1970,10 @@ int b200_extra_load(const char * path, int device, b200_extra_t ** out) {
         const GgjtTensor & tn = f.get("norm.weight", {E});
         const GgjtTensor & to = f.get("output.weight", {E, V});
         e->emb_type = (int) te.type; e->out_type = (int) to.type;
-        if (te.type != GT_Q4_0 && te.type != GT_Q8_0 && te.type != GT_F16 && te.type != GT_F32)
+        if (te.type != GT_Q4_0 && te.type != GT_Q4_1 && te.type != GT_Q8_0 && te.type != GT_F16 && te.type != GT_F32)
             return fail(B200_EFILE, "tok_embeddings type %u unsupported", te.type);
-        if (to.type != GT_Q4_0 && to.type != GT_Q8_0 && to.type != GT_F16 && to.type != GT_Q6_K)
-            return fail(B200_EFILE, "output.weight type %u unsupported (Q4_0, Q8_0, F16, Q6_K)", to.type);
+        if (to.type != GT_Q4_0 && to.type != GT_Q4_1 && to.type != GT_Q8_0 && to.type != GT_F16 && to.type != GT_Q6_K)
+            return fail(B200_EFILE, "output.weight type %u unsupported (Q4_0, Q4_1, Q8_0, F16, Q6_K)", to.type);
         if (to.type == GT_Q6_K && E % 256) return fail(B200_EFILE, "Q6_K output.weight needs n_embd %% 256 == 0");
         if (tn.type != GT_F32) return fail(B200_EFILE, "norm.weight must be F32");
         if ((rc = dev_alloc(s, &e->emb_raw, te.nbytes)) || (rc = dev_alloc(s, &e->norm_w, (size_t) E))) return rc;

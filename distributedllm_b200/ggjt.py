@@ -31,7 +31,7 @@ NO_FIRST_LAYER = 0xFFFFFFFF
 # ggml.h:265-281
 T_F32, T_F16, T_Q4_0, T_Q4_1, T_Q8_0, T_Q6_K = 0, 1, 2, 3, 8, 14
 # llama.h:108-115
-FTYPE_F32, FTYPE_F16, FTYPE_Q4_0, FTYPE_Q8_0 = 0, 1, 2, 7
+FTYPE_F32, FTYPE_F16, FTYPE_Q4_0, FTYPE_Q4_1, FTYPE_Q8_0 = 0, 1, 2, 3, 7
 
 QK = 32
 TYPE_BLOCK = {T_F32: (1, 4), T_F16: (1, 2), T_Q4_0: (32, 18), T_Q4_1: (32, 20),
@@ -84,6 +84,35 @@ def dequantize_q4_0(blocks: np.ndarray) -> np.ndarray:
     return w.reshape(rows, nb * QK)
 
 
+def quantize_q4_1(x: np.ndarray) -> np.ndarray:
+    """[rows, K] f32 -> [rows, K/32, 20] u8 (fp16 d, fp16 min, 16 nibble bytes). ggml.c:982-1015."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    rows, k = x.shape
+    assert k % QK == 0
+    xb = x.reshape(rows, k // QK, QK)
+    mn, mx = xb.min(axis=2), xb.max(axis=2)
+    d = ((mx - mn) / np.float32(15)).astype(np.float32)
+    idv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, np.float32(1)), np.float32(0)).astype(np.float32)
+    xs = ((xb - mn[..., None]).astype(np.float32) * idv[..., None]).astype(np.float32)
+    q = np.minimum(15, np.trunc((xs + np.float32(0.5)).astype(np.float32)).astype(np.int32)).astype(np.uint8)
+    out = np.empty((rows, k // QK, 20), dtype=np.uint8)
+    out[..., 0:2] = d.astype(np.float16).view(np.uint8).reshape(rows, k // QK, 2)
+    out[..., 2:4] = mn.astype(np.float16).view(np.uint8).reshape(rows, k // QK, 2)
+    out[..., 4:] = q[..., :16] | (q[..., 16:] << 4)
+    return out
+
+
+def dequantize_q4_1(blocks: np.ndarray) -> np.ndarray:
+    """[rows, nb, 20] u8 -> [rows, nb*32] f32: nibble * d + m, two roundings (ggml.c:1543-1562)."""
+    rows, nb, _ = blocks.shape
+    d = blocks[..., 0:2].copy().view(np.float16).astype(np.float32)
+    m = blocks[..., 2:4].copy().view(np.float16).astype(np.float32)
+    qs = blocks[..., 4:]
+    n = np.concatenate([qs & 0x0F, qs >> 4], axis=2).astype(np.float32)
+    w = ((n * d).astype(np.float32) + m).astype(np.float32)
+    return w.reshape(rows, nb * QK)
+
+
 def quantize_q8_0(x: np.ndarray) -> np.ndarray:
     """[rows, K] f32 -> [rows, K/32, 34] u8. ggml.c:1100-1140 (reference variant: id=1/d, roundf)."""
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -107,6 +136,8 @@ def encode_tensor(x: np.ndarray, ttype: int) -> bytes:
         return np.ascontiguousarray(x, dtype=np.float32).astype(np.float16).tobytes()
     if ttype == T_Q4_0:
         return quantize_q4_0(x).tobytes()
+    if ttype == T_Q4_1:
+        return quantize_q4_1(x).tobytes()
     if ttype == T_Q8_0:
         return quantize_q8_0(x).tobytes()
     raise ValueError(f"cannot encode ggml type {ttype}")
@@ -352,7 +383,7 @@ def synth_layer_tensors(shape: ModelShape, layer: int, wtype: int, seed: int):
             yield pre + nm, wtype, (k, rows), encode_tensor(w, wtype)
 
 
-_FTYPE_OF = {T_F32: FTYPE_F32, T_F16: FTYPE_F16, T_Q4_0: FTYPE_Q4_0, T_Q8_0: FTYPE_Q8_0}
+_FTYPE_OF = {T_F32: FTYPE_F32, T_F16: FTYPE_F16, T_Q4_0: FTYPE_Q4_0, T_Q4_1: FTYPE_Q4_1, T_Q8_0: FTYPE_Q8_0}
 
 
 def write_synth_slice(path: str, shape: ModelShape, layer_from: int, layer_to: int, wtype: int = T_Q4_0,

@@ -60,6 +60,9 @@ def port_lib() -> C.CDLL:
         L.orc_dot_q4_0_q8_0.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_dot_q8_0_q8_0.restype = C.c_float
         L.orc_dot_q8_0_q8_0.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_dot_q4_1_q8_1.restype = C.c_float
+        L.orc_dot_q4_1_q8_1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_quant_q8_1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_dot_f16.restype = C.c_float
         L.orc_dot_f16.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int]
         L.orc_quant_q8_0.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

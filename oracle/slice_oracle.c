@@ -16,6 +16,8 @@
  * orc_quant_q8_0      quantize_row_q8_0, AVX branch (ggml.c:1215-1252)
  * orc_dot_q4_0_q8_0   ggml_vec_dot_q4_0_q8_0, AVX2 branch (ggml.c:2432-2455) + hsum_float_8 (614-620)
  * orc_dot_q8_0_q8_0   ggml_vec_dot_q8_0_q8_0, AVX2 branch (ggml.c:3313-3335)
+ * orc_quant_q8_1      quantize_row_q8_1, AVX2 branch (ggml.c:1426-1484): d stays f32, s = d * sum(q)
+ * orc_dot_q4_1_q8_1   ggml_vec_dot_q4_1_q8_1, AVX2 branch (ggml.c:2700-2733): the min term is a scalar float chain
  * orc_dot_f16         ggml_vec_dot_f16 (ggml.c:2323-2357) with GGML_F32x8_REDUCE (1895-1913)
  * orc_rmsnorm         ggml_compute_forward_rms_norm_f32 (ggml.c:10309-10352) + ggml_mul (9062)
  * orc_rope            ggml_compute_forward_rope_f32, mode 0 (ggml.c:11956-12055)
@@ -29,7 +31,7 @@
 #include <string.h>
 
 #define QK 32
-enum { W_F32 = 0, W_F16 = 1, W_Q4_0 = 2, W_Q8_0 = 8 };
+enum { W_F32 = 0, W_F16 = 1, W_Q4_0 = 2, W_Q4_1 = 3, W_Q8_0 = 8 };
 
 /* ---------------------------------------------------------------- fp16 <-> fp32 (software, IEEE RNE) */
 static float h2f(uint16_t h) {
@@ -85,6 +87,19 @@ void orc_quant_q8_0(const float * x, int k, int8_t * q, uint16_t * d) {
     }
 }
 
+/* Q8_1: the block scale is NOT rounded to fp16, and s = d * (sum of the 32 quants) rides along for Q4_1's min term */
+void orc_quant_q8_1(const float * x, int k, int8_t * q, float * d, float * s) {
+    for (int b = 0; b < k / QK; b++) {
+        float amax = 0.0f;
+        for (int j = 0; j < QK; j++) { float a = fabsf(x[b*QK + j]); if (a > amax) amax = a; }
+        d[b] = amax / 127.f;
+        const float id = (amax != 0.0f) ? 127.f / amax : 0.0f;
+        int sum = 0;
+        for (int j = 0; j < QK; j++) { q[b*QK + j] = (int8_t) lrintf(x[b*QK + j] * id); sum += q[b*QK + j]; }
+        s[b] = d[b] * (float) sum;
+    }
+}
+
 static float hsum8(const float a[8]) {            /* hsum_float_8, ggml.c:614-620 */
     float r0 = a[4] + a[0], r1 = a[5] + a[1], r2 = a[6] + a[2], r3 = a[7] + a[3];
     r0 = r0 + r2; r1 = r1 + r3;
@@ -108,6 +123,27 @@ float orc_dot_q4_0_q8_0(const uint8_t * w, const int8_t * aq, const uint16_t * a
         }
     }
     return hsum8(acc);
+}
+
+/* one row of Q4_1 blocks (20 B: fp16 d, fp16 m, 16 nibble bytes) . one Q8_1-quantised activation row */
+float orc_dot_q4_1_q8_1(const uint8_t * w, const int8_t * aq, const float * ad, const float * as, int k) {
+    float acc[8] = {0};
+    float summs = 0.0f;
+    for (int b = 0; b < k / QK; b++) {
+        const uint8_t * blk = w + (size_t) b * 20; uint16_t dw, mw; memcpy(&dw, blk, 2); memcpy(&mw, blk + 2, 2);
+        const float d = h2f(dw) * ad[b];
+        summs += h2f(mw) * as[b];                      /* two roundings: -std=c11 builds do not contract */
+        for (int l = 0; l < 8; l++) {
+            int s = 0;
+            for (int j = 0; j < 4; j++) {
+                int e = 4*l + j;
+                int wv = e < 16 ? (blk[4 + e] & 0x0F) : (blk[4 + e - 16] >> 4);
+                s += wv * (int) aq[b*QK + e];
+            }
+            acc[l] = fmaf(d, (float) s, acc[l]);
+        }
+    }
+    return hsum8(acc) + summs;
 }
 
 float orc_dot_q8_0_q8_0(const uint8_t * w, const int8_t * aq, const uint16_t * ad, int k) {
@@ -244,6 +280,15 @@ static void matmul(const orc_slice * s, const uint8_t * W, int rows, int k, cons
                     ? orc_dot_q4_0_q8_0(W + r * rb, aq + (size_t) n * k, ad + (size_t) n * nb, k)
                     : orc_dot_q8_0_q8_0(W + r * rb, aq + (size_t) n * k, ad + (size_t) n * nb, k);
         free(aq); free(ad);
+    } else if (s->wtype == W_Q4_1) {
+        int8_t * aq = malloc((size_t) N * k); float * ad = malloc((size_t) N * nb * 4), * as = malloc((size_t) N * nb * 4);
+        for (int n = 0; n < N; n++) orc_quant_q8_1(x + (size_t) n * k, k, aq + (size_t) n * k, ad + (size_t) n * nb, as + (size_t) n * nb);
+        const size_t rb = (size_t) nb * 20;
+        #pragma omp parallel for schedule(static)
+        for (int r = 0; r < rows; r++)
+            for (int n = 0; n < N; n++)
+                y[(size_t) n * rows + r] = orc_dot_q4_1_q8_1(W + r * rb, aq + (size_t) n * k, ad + (size_t) n * nb, as + (size_t) n * nb, k);
+        free(aq); free(ad); free(as);
     } else if (s->wtype == W_F16) {
         uint16_t * xh = malloc((size_t) N * k * 2);
         for (size_t i = 0; i < (size_t) N * k; i++) xh[i] = f2h(x[i]);

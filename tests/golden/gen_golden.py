@@ -2,6 +2,7 @@
 
   slices.npz     hidden states of oracle/_ref (= distllm/tensor_processor.cpp compiled unmodified, see
                  oracle/Makefile) on seeded synthetic slice files, for a fixed schedule of propagate_forward calls
+  slices_q4_1.*  the same for Q4_1 slices (added later; `gen_golden.py q4_1` writes only these) + extra_q4_1.npz
   extra.npz      reference get_inputs / get_llm_output / llama_tokenize on a synthetic extra-layers file
   tokenizer.json reference tokenisation of fixed strings with vendor/llama.cpp/models/ggml-vocab.bin's vocabulary
   protocol.json  frames produced by the reference's distllm/protocol.py for one instance of every message
@@ -31,13 +32,17 @@ CASES = [  # name, shape, weight type, layer range, schedule of calls
     ("tiny_q8_0", "tiny", ggjt.T_Q8_0, (0, 1), [18, 1, 1, 16]),
     ("tiny_f16", "tiny", ggjt.T_F16, (2, 3), [35, 1, 1]),
 ]
+CASES_Q4_1 = [
+    ("tiny_q4_1", "tiny", ggjt.T_Q4_1, (1, 2), [40, 1, 1, 7, 1, 20, 3, 1]),
+    ("tiny128_q4_1", "tiny128", ggjt.T_Q4_1, (0, 1), [33, 1, 1, 1, 30, 1]),
+    ("tiny3b_q4_1", "tiny3b", ggjt.T_Q4_1, (0, 1), [37, 1, 1, 5]),
+]
 
 
-def main():
-    tmp = tempfile.mkdtemp()
+def gen_slices(tmp, cases, stem):
     out = {}
     meta = {}
-    for name, shape, wt, (a, b), sched in CASES:
+    for name, shape, wt, (a, b), sched in cases:
         sh = ggjt.SHAPES[shape]
         path = os.path.join(tmp, name + ".bin")
         ggjt.write_synth_slice(path, sh, a, b, wt, seed=0)
@@ -50,8 +55,30 @@ def main():
             out["%s/x%d" % (name, i)] = x
             out["%s/y%d" % (name, i)] = ref.forward(x)
         ref.close()
-    np.savez_compressed(os.path.join(HERE, "slices.npz"), **out)
-    json.dump(meta, open(os.path.join(HERE, "slices.json"), "w"), indent=1)
+    np.savez_compressed(os.path.join(HERE, stem + ".npz"), **out)
+    json.dump(meta, open(os.path.join(HERE, stem + ".json"), "w"), indent=1)
+
+
+def gen_q4_1(tmp):
+    gen_slices(tmp, CASES_Q4_1, "slices_q4_1")
+    # client side of a Q4_1 model: tok_embeddings rows dequantised as nibble * d + m, output.weight through the Q4_1 dot
+    sh = ggjt.SHAPES["tiny"]
+    extra = os.path.join(tmp, "extra_q4_1.bin")
+    ggjt.write_synth_extra(extra, sh, ggjt.T_Q4_1, seed=0)
+    toks = np.array([1, 5, 300, 44, 511, 0, 77], np.int32)
+    h = np.random.default_rng(7).standard_normal((5, sh.n_embd), dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "extra_q4_1.npz"), tokens=toks, emb=oracle.ref_embed(extra, toks, sh.n_embd), hidden=h,
+                        logits_all=oracle.ref_logits(extra, h, sh.n_vocab, True),
+                        file_sha256=np.frombuffer(hashlib.sha256(open(extra, "rb").read()).digest(), np.uint8))
+
+
+def main():
+    tmp = tempfile.mkdtemp()
+    if sys.argv[1:] == ["q4_1"]:
+        gen_q4_1(tmp)
+        return
+    gen_slices(tmp, CASES, "slices")
+    gen_q4_1(tmp)
 
     # extra layers + tokenizer on a synthetic all-Q4_0 extra file
     sh = ggjt.SHAPES["tiny"]

@@ -71,6 +71,20 @@ def test_extra_layers_match_reference_goldens(llm, tmp_path):
     assert llm.decode_token(extra, 1) == "<s>"
 
 
+def test_q4_1_extra_layers_match_reference_goldens(llm, tmp_path):
+    """Client side of a `quantize q4_1` model whose n_embd is not a multiple of 256: tok_embeddings rows are nibble * d + m,
+    output.weight goes through the Q4_1 x Q8_1 dot."""
+    g = np.load(os.path.join(GOLD, "extra_q4_1.npz"))
+    sh = ggjt.SHAPES["tiny"]
+    extra = str(tmp_path / "extra.bin")
+    ggjt.write_synth_extra(extra, sh, ggjt.T_Q4_1, seed=0)
+    emb = np.array(llm.prepare_embeddings(extra, g["tokens"].tolist()), np.float32).reshape(-1, sh.n_embd)
+    assert (_bits(emb) == _bits(g["emb"])).all()
+    hid = g["hidden"]
+    la = np.array(llm.get_logits(extra, hid.ravel().tolist(), True), np.float32).reshape(len(hid), -1)
+    assert (_bits(la) == _bits(g["logits_all"])).all(), int((_bits(la) != _bits(g["logits_all"])).sum())
+
+
 def test_q6k_lm_head_matches_reference_goldens(llm):
     """The extra-layers file exactly as the reference's `quantize q4_0` + `slice_model extra_layers` produce it
     (Q6_K output.weight): logits bit-identical to the reference's get_llm_output."""
@@ -174,7 +188,9 @@ def test_goldens_on_gpu(tmp_path):
     """The committed reference goldens, replayed on the GPU."""
     from distributedllm_b200 import capi
     meta = json.load(open(os.path.join(GOLD, "slices.json")))
-    data = np.load(os.path.join(GOLD, "slices.npz"))
+    meta.update(json.load(open(os.path.join(GOLD, "slices_q4_1.json"))))
+    data = dict(np.load(os.path.join(GOLD, "slices.npz")))
+    data.update(np.load(os.path.join(GOLD, "slices_q4_1.npz")))
     for name, m in meta.items():
         sh = ggjt.SHAPES[m["shape"]]
         path = str(tmp_path / (name + ".bin"))

@@ -38,7 +38,8 @@ def _run_pair(path, calls, shape, n_ctx=512, seed=1):
 
 @pytest.mark.parametrize("shape,wtype", [("tiny", ggjt.T_Q4_0), ("tiny128", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q4_0),
                                          ("tiny", ggjt.T_Q8_0), ("tiny128", ggjt.T_Q8_0), ("tiny", ggjt.T_F16),
-                                         ("tiny3b", ggjt.T_F16), ("tiny128", ggjt.T_F16)])
+                                         ("tiny3b", ggjt.T_F16), ("tiny128", ggjt.T_F16),
+                                         ("tiny", ggjt.T_Q4_1), ("tiny128", ggjt.T_Q4_1), ("tiny3b", ggjt.T_Q4_1)])
 def test_bit_exact_prefill_then_decode(tmp_models, shape, wtype):
     sh = ggjt.SHAPES[shape]
     path = tmp_models(shape, wtype, 1, 2)
@@ -55,10 +56,10 @@ def test_ring_and_simple_kernels_agree(tmp_models, monkeypatch):
         assert bad == 0, "ring=%s: %d of %d floats differ" % (ring, bad, tot)
 
 
-@pytest.mark.parametrize("shape", ["tiny", "tiny128"])
-def test_decode_only_long(tmp_models, shape):
+@pytest.mark.parametrize("shape,wtype", [("tiny", ggjt.T_Q4_0), ("tiny128", ggjt.T_Q4_0), ("tiny128", ggjt.T_Q4_1)])
+def test_decode_only_long(tmp_models, shape, wtype):
     sh = ggjt.SHAPES[shape]
-    path = tmp_models(shape, ggjt.T_Q4_0, 0, 2)
+    path = tmp_models(shape, wtype, 0, 2)
     bad, tot = _run_pair(path, [1] * 40, sh)
     assert bad == 0
 
@@ -76,8 +77,23 @@ def test_launch_modes_agree(tmp_models, monkeypatch, pdl, graph, nq):
     assert bad == 0
 
 
+@pytest.mark.parametrize("ring,nq", [("1", "0"), ("0", "0"), ("0", "1")])
+def test_q4_1_launch_modes_agree(tmp_models, monkeypatch, ring, nq):
+    """Q4_1 slices (unsigned nibbles + the scalar min chain, Q8_1 activations): the fused RMSNorm prologue (B200_NQ=0), the
+    grid-barrier epilogue and the ring-less kernels are the same arithmetic."""
+    monkeypatch.setenv("B200_RING", ring)
+    monkeypatch.setenv("B200_NQ", nq)
+    sh = ggjt.SHAPES["tiny3b"]
+    path = tmp_models("tiny3b", ggjt.T_Q4_1, 0, 2)
+    bad, tot = _run_pair(path, [21, 1, 1, 1, 9, 1], sh)
+    assert bad == 0, "%d of %d floats differ" % (bad, tot)
+    path = tmp_models("tiny128", ggjt.T_Q4_1, 0, 1)
+    bad, tot = _run_pair(path, [1, 1, 1, 40, 1], ggjt.SHAPES["tiny128"])
+    assert bad == 0, "%d of %d floats differ" % (bad, tot)
+
+
 @pytest.mark.parametrize("nc", ["8", "4", "2"])
-@pytest.mark.parametrize("shape,wtype", [("tiny128", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q8_0)])
+@pytest.mark.parametrize("shape,wtype", [("tiny128", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q8_0), ("tiny128", ggjt.T_Q4_1)])
 def test_columns_per_cta_is_a_scheduling_choice(tmp_models, monkeypatch, nc, shape, wtype):
     """Multi-token calls pick 8 / 4 / 2 columns per CTA from the matrix width and the batch; columns never interact."""
     monkeypatch.setenv("B200_NC", nc)

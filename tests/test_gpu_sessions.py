@@ -14,7 +14,7 @@ def _bits(a):
 
 
 @pytest.mark.parametrize("shape,wtype", [("tiny128", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q4_0), ("tiny128", ggjt.T_Q8_0),
-                                         ("tiny", ggjt.T_F16)])
+                                         ("tiny", ggjt.T_F16), ("tiny128", ggjt.T_Q4_1)])
 def test_batched_step_equals_private_contexts(tmp_models, shape, wtype):
     from distributedllm_b200 import capi
     from oracle import oracle

@@ -13,7 +13,9 @@ from oracle import oracle
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 META = json.load(open(os.path.join(GOLD, "slices.json")))
-DATA = np.load(os.path.join(GOLD, "slices.npz"))
+META.update(json.load(open(os.path.join(GOLD, "slices_q4_1.json"))))
+DATA = dict(np.load(os.path.join(GOLD, "slices.npz")))
+DATA.update(np.load(os.path.join(GOLD, "slices_q4_1.npz")))
 
 
 def _bits(a):
@@ -37,7 +39,8 @@ def test_port_matches_reference_goldens(name, tmp_path):
 
 
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
-@pytest.mark.parametrize("shape,wtype", [("tiny", ggjt.T_F32), ("tiny128", ggjt.T_F16), ("tiny3b", ggjt.T_Q8_0)])
+@pytest.mark.parametrize("shape,wtype", [("tiny", ggjt.T_F32), ("tiny128", ggjt.T_F16), ("tiny3b", ggjt.T_Q8_0),
+                                         ("tiny3b", ggjt.T_Q4_1)])
 def test_port_matches_live_reference(shape, wtype, tmp_path):
     sh = ggjt.SHAPES[shape]
     path = str(tmp_path / "m.bin")
@@ -89,3 +92,38 @@ def test_q8_0_activation_quant_matches_survey_recipe():
     assert (d == (m / np.float32(127)).astype(np.float16).view(np.uint16)).all()
     idv = np.where(m != 0, np.float32(127) / np.where(m != 0, m, 1), 0).astype(np.float32)
     assert (q.reshape(8, 32) == np.rint((xb * idv[:, None]).astype(np.float32)).astype(np.int8)).all()
+
+
+def test_q4_1_dot_is_scale_chain_plus_min_chain():
+    """ggml_vec_dot_q4_1_q8_1 (ggml.c:2700-2733): unsigned nibbles, 8 fma lanes with d0*d1 (d1 NOT rounded to fp16), and
+    the min term m*s added block by block as a scalar float; Q8_1's s = d * sum(q) (ggml.c:1472)."""
+    L = oracle.port_lib()
+    rng = np.random.default_rng(9)
+    k = 128
+    w = ggjt.quantize_q4_1(rng.standard_normal((1, k)).astype(np.float32) + 0.3)
+    x = rng.standard_normal(k).astype(np.float32)
+    x[32:64] = 0
+    q, d, s = np.zeros(k, np.int8), np.zeros(k // 32, np.float32), np.zeros(k // 32, np.float32)
+    L.orc_quant_q8_1(x.ctypes.data, k, q.ctypes.data, d.ctypes.data, s.ctypes.data)
+    amax = np.abs(x.reshape(-1, 32)).max(1).astype(np.float32)
+    assert (d.view(np.uint32) == (amax / np.float32(127)).astype(np.float32).view(np.uint32)).all()
+    assert (s.view(np.uint32) == (d * q.reshape(-1, 32).sum(1).astype(np.float32)).astype(np.float32).view(np.uint32)).all()
+    got = L.orc_dot_q4_1_q8_1(w.ctypes.data, q.ctypes.data, d.ctypes.data, s.ctypes.data, k)
+    blocks = w.reshape(-1, 20)
+    acc, summs = np.zeros(8, np.float32), np.float32(0)
+    for b in range(k // 32):
+        d0 = blocks[b, 0:2].copy().view(np.float16).astype(np.float32)[0]
+        m0 = blocks[b, 2:4].copy().view(np.float16).astype(np.float32)[0]
+        nib = np.concatenate([blocks[b, 4:] & 0x0F, blocks[b, 4:] >> 4]).astype(np.int32)
+        summs = np.float32(summs + np.float32(m0 * s[b]))
+        si = (nib * q[b * 32:(b + 1) * 32].astype(np.int32)).reshape(8, 4).sum(1)
+        dd = np.float32(d0 * d[b])
+        acc = (dd.astype(np.float64) * si.astype(np.float64) + acc.astype(np.float64)).astype(np.float32)   # fma: one rounding
+    r0, r1, r2, r3 = (np.float32(acc[i + 4] + acc[i]) for i in range(4))
+    want = np.float32(np.float32(np.float32(r0 + r2) + np.float32(r1 + r3)) + summs)
+    assert np.float32(got).view(np.uint32) == want.view(np.uint32)
+    # and the file-format side: the numpy quantiser's blocks decode to within one step of the input
+    xw = rng.standard_normal((4, 64)).astype(np.float32)
+    blk = ggjt.quantize_q4_1(xw)
+    step = (xw.reshape(4, 2, 32).max(2) - xw.reshape(4, 2, 32).min(2)) / 15
+    assert (np.abs(ggjt.dequantize_q4_1(blk) - xw).reshape(4, 2, 32).max(2) <= step * 0.51 + 2e-3).all()
