@@ -453,21 +453,39 @@ def _fast_q4_pool(seed: int, k: int) -> np.ndarray:
     return blocks
 
 
-def write_fast_q4_slice(path: str, shape: ModelShape, layer_from: int, layer_to: int, seed: int = 0) -> int:
+def _fast_q41_pool(seed: int, k: int) -> np.ndarray:
+    """Q4_1 twin of _fast_q4_pool: 20-byte blocks, fp16 step d = mag*(1 + j/512) > 0 and fp16 minimum
+    m = -(7.5 + i/256)*d (i in [-128,128)), so nibble*d + m is centred with std ~ 1/sqrt(fan_in)."""
+    rng = np.random.default_rng([seed, k, 79])
+    blocks = rng.integers(0, 256, size=(_POOL_BLOCKS, 20), dtype=np.uint8)
+    mag = 1.0 / (4.6 * np.sqrt(k))
+    d = (mag * (1.0 + (blocks[:, 1].astype(np.float32) - 128.0) / 512.0)).astype(np.float16)
+    m = (-(7.5 + (blocks[:, 3].astype(np.float32) - 128.0) / 256.0) * d.astype(np.float32)).astype(np.float16)
+    blocks[:, 0:2] = d.view(np.uint8).reshape(-1, 2)
+    blocks[:, 2:4] = m.view(np.uint8).reshape(-1, 2)
+    return blocks
+
+
+def write_fast_q4_slice(path: str, shape: ModelShape, layer_from: int, layer_to: int, seed: int = 0,
+                        wtype: int = T_Q4_0) -> int:
     """Large-model generator for benchmarks.  Quantising 6.5e9 Gaussians takes minutes, so Q4_0
     blocks are written directly: each matrix is a window (at a per-tensor pseudo-random block
     offset, wrapping) into a 36 MiB pool of random blocks built once per fan-in.  The file is the
     ground truth for both the B200 path and the CPU reference, so the distribution only has to keep
-    activations finite; any layer range of the same (shape, seed) is reproducible.  Returns bytes written."""
+    activations finite; any layer range of the same (shape, seed) is reproducible.  Returns bytes written.
+    `wtype` = T_Q4_1 writes 20-byte Q4_1 blocks from _fast_q41_pool instead."""
+    assert wtype in (T_Q4_0, T_Q4_1)
+    bsz = TYPE_BLOCK[wtype][1]
     vocab = default_vocab(shape.n_vocab)
     hp = HParams(shape.n_vocab, shape.n_embd, shape.n_mult, shape.n_head, layer_to - layer_from + 1,
-                 shape.n_embd // shape.n_head, FTYPE_Q4_0, layer_from)
+                 shape.n_embd // shape.n_head, _FTYPE_OF[wtype], layer_from)
     e, ff = shape.n_embd, shape.n_ff
     dims = {"attention.wq.weight": (e, e), "attention.wk.weight": (e, e), "attention.wv.weight": (e, e),
             "attention.wo.weight": (e, e), "feed_forward.w1.weight": (ff, e), "feed_forward.w2.weight": (e, ff),
             "feed_forward.w3.weight": (ff, e)}
-    pools = {k: memoryview(_fast_q4_pool(seed, k)).cast("B") for k in sorted({e, ff})}
-    pool_bytes = _POOL_BLOCKS * 18
+    make_pool = _fast_q4_pool if wtype == T_Q4_0 else _fast_q41_pool
+    pools = {k: memoryview(make_pool(seed, k)).cast("B") for k in sorted({e, ff})}
+    pool_bytes = _POOL_BLOCKS * bsz
     with open(path, "wb") as f:
         _write_header(f, hp, vocab)
         for layer in range(layer_from, layer_to + 1):
@@ -479,10 +497,10 @@ def write_fast_q4_slice(path: str, shape: ModelShape, layer_from: int, layer_to:
                     _write_tensor(f, pre + nm, T_F32, (e,), w.tobytes())
                     continue
                 rows, k = dims[nm]
-                nbytes = rows * k // QK * 18
-                start = int(rng.integers(0, _POOL_BLOCKS)) * 18
+                nbytes = rows * k // QK * bsz
+                start = int(rng.integers(0, _POOL_BLOCKS)) * bsz
                 name = (pre + nm).encode("utf-8")
-                f.write(struct.pack("<III", 2, len(name), T_Q4_0))
+                f.write(struct.pack("<III", 2, len(name), wtype))
                 f.write(struct.pack("<2I", k, rows))
                 f.write(name)
                 f.write(b"\0" * ((-f.tell()) & 31))

@@ -96,8 +96,50 @@ def config5():
     return out
 
 
+def config_q4_1():
+    """Not a BASELINE config: the reference's other provisioning choice (`quantize q4_1`, provision.py:179), 7B, 8-layer slice,
+    decode at p~270 against the same slice in Q4_0, and a parity spot check of the big shapes against the CPU oracle."""
+    from oracle import oracle
+    sh = ggjt.SHAPES["7b"]
+    L = 8
+    out = {"config": "LLaMA-7B Q4_1 vs Q4_0, %d-layer slice, n_ctx 512, decode at p~270" % L, "peak_gbs": PEAK}
+    for tag, wt in (("q4_1", ggjt.T_Q4_1), ("q4_0", ggjt.T_Q4_0)):
+        p = os.path.join(bench.model_dir(), "7b_%s_layers_0_%d.bin" % (tag, L - 1))
+        if not os.path.isfile(p):
+            ggjt.write_fast_q4_slice(p + ".tmp", sh, 0, L - 1, 0, wtype=wt)
+            os.replace(p + ".tmp", p)
+        sl = capi.Slice(p, 0, 512)
+        x = bench.synth_inputs(256, sl.n_embd, 5)
+        for i in range(0, 256, 64):
+            sl.forward(x[i:i + 64])
+        bench._h2d(sl, x[0:1])
+        steps = 32
+        ms = timed(sl, lambda: sl.forward_device(sl.dev_in, 1, sl.dev_out), steps)
+        pos = 256 + 3 + steps / 2
+        byts = sl.info.weight_bytes + sl.info.kv_bytes_per_pos * pos
+        out[tag] = {"us_per_layer": 1e3 * ms / L, "tokens_per_s_32_layers_equiv": 1e3 / (ms * 32 / L),
+                    "achieved_gbs": byts / (ms * 1e-3) / 1e9, "frac": byts / (ms * 1e-3) / 1e9 / PEAK, "weight_bytes": sl.info.weight_bytes}
+        sl.close()
+        if wt == ggjt.T_Q4_1:
+            # parity at the full 7B widths: a 2-layer slice, prompt of 9 + 3 single-token steps, against the C restatement
+            p2 = os.path.join(bench.model_dir(), "7b_q4_1_layers_0_1.bin")
+            if not os.path.isfile(p2):
+                ggjt.write_fast_q4_slice(p2 + ".tmp", sh, 0, 1, 0, wtype=wt)
+                os.replace(p2 + ".tmp", p2)
+            g, c = capi.Slice(p2, 0, 64), oracle.PortSlice(p2, 64)
+            bad = 0
+            for n in (9, 1, 1, 1):
+                xx = bench.synth_inputs(n, g.n_embd, 40 + n)
+                bad += int((np.ascontiguousarray(g.forward(xx)).view(np.uint32) != np.ascontiguousarray(c.forward(xx)).view(np.uint32)).sum())
+            out["parity_mismatches_7b_2_layers"] = bad
+            g.close()
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["4", "5"]
+    if "q4_1" in which:
+        print(json.dumps(config_q4_1()))
     if "5" in which:
         print(json.dumps(config5()))
     if "4" in which:

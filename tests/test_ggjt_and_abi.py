@@ -132,3 +132,24 @@ def test_fast_writers_produce_loadable_reference_format_files(tmp_path):
     ggjt.write_fast_q4_extra(ex, sh, seed=7)
     e = ggjt.read_file(ex, sliced=True)
     assert list(e.tensors) == ["tok_embeddings.weight", "norm.weight", "output.weight"] and e.hparams.n_layer == 0
+
+
+def test_q4_1_quantizer_is_the_reference_quantize_tool(tmp_path):
+    """ggjt.quantize_q4_1 (ggml.c:982-1015 restated) against the reference's own `quantize ... q4_1` binary, byte for byte."""
+    import subprocess
+    from oracle import oracle
+    tool = os.path.join(oracle.REF_DIR, "quantize")
+    if not os.path.isfile(tool):
+        pytest.skip("oracle/_ref/quantize not built")
+    sh = ggjt.SHAPES["tiny3b"]                                   # n_embd = 800: output.weight stays Q4_1 (not Q6_K)
+    full, fq = str(tmp_path / "f32.bin"), str(tmp_path / "q41.bin")
+    ggjt.write_synth_full(full, sh, ggjt.T_F32, seed=0)
+    subprocess.run([tool, full, fq, "q4_1"], check=True, capture_output=True)
+    a, b = ggjt.read_file(full), ggjt.read_file(fq)
+    n = 0
+    for name, t in b.tensors.items():
+        if t.ttype == ggjt.T_Q4_1:
+            src = np.frombuffer(a.read_raw(name), np.float32).reshape(t.ne[1], t.ne[0])
+            assert ggjt.quantize_q4_1(src).tobytes() == b.read_raw(name), name
+            n += 1
+    assert n == 2 + 7 * sh.n_layer
