@@ -20,10 +20,11 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 sh = ggjt.SHAPES["tiny128"]
 d = %(tmp)r
+WT = int(os.environ.get("B200_TEST_WTYPE", str(ggjt.T_Q4_0)))
 a, b = layer_ranges(sh.n_layer, world)[rank]
 p = os.path.join(d, "s_%%d_%%d.bin" %% (a, b))
 if not os.path.exists(p):
-    ggjt.write_synth_slice(p, sh, a, b, ggjt.T_Q4_0, seed=0)
+    ggjt.write_synth_slice(p, sh, a, b, WT, seed=0)
 sl = capi.Slice(p, local, 64, n_sessions=4)
 lib = capi.lib()
 from distributedllm_b200.pipeline import join_pipeline, torch_collectives
@@ -41,7 +42,7 @@ cudart = _Rt()
 rng = np.random.default_rng(21)
 ok = True
 if rank == 0:
-    whole = os.path.join(d, "whole.bin"); ggjt.write_synth_slice(whole, sh, 0, sh.n_layer - 1, ggjt.T_Q4_0, seed=0)
+    whole = os.path.join(d, "whole.bin"); ggjt.write_synth_slice(whole, sh, 0, sh.n_layer - 1, WT, seed=0)
     ref = capi.Slice(whole, local, 64, n_sessions=4)
 for n in (7, 1, 1, 5, 1):
     x = rng.standard_normal((n, sh.n_embd), dtype=np.float32)
@@ -135,16 +136,17 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("peer,fold", [(1, 1), (1, 0), (0, 0)], ids=["peer-folded-into-matmuls", "peer-send-recv-kernels", "nccl"])
-def test_two_gpu_pipeline_bit_exact(tmp_path, peer, fold):
+@pytest.mark.parametrize("peer,fold,wtype", [(1, 1, 2), (1, 0, 2), (0, 0, 2), (1, 1, 3)],
+                         ids=["peer-folded-into-matmuls", "peer-send-recv-kernels", "nccl", "peer-folded-q4_1"])
+def test_two_gpu_pipeline_bit_exact(tmp_path, peer, fold, wtype):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT, "tmp": str(tmp_path)})
-    env = dict(os.environ, B200_PP_PEER=str(peer), B200_PP_FOLD=str(fold))
+    env = dict(os.environ, B200_PP_PEER=str(peer), B200_PP_FOLD=str(fold), B200_TEST_WTYPE=str(wtype))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", str(29533 + 2 * peer + fold), str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(29533 + 2 * peer + fold + 4 * (wtype == 3)), str(script)],
                          capture_output=True, text=True, timeout=600, env=env)
     assert "PIPELINE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
     assert ("transport=peer" if peer else "transport=nccl") in out.stdout, out.stdout[-500:]
