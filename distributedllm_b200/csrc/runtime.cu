@@ -66,7 +66,7 @@ struct b200_slice {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
     int64_t launches = 0, weight_bytes = 0;
-    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true, f16_ring = true, use_tiled_attn = true;
+    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true, f16_ring = true, use_tiled_attn = true, use_n8 = false;
     bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
     int fast_version = 2;                                                               // 2: fastgemm2.cuh (TMA tensor map, N = 256), 1: fastgemm.cuh
@@ -177,6 +177,58 @@ static int launch_gemv_t(b200_slice * s, GemvArgs a) {
     prof_end(s);
     s->launches++;
     return 0;
+}
+
+// narrow matrices of a single-token step: 8 threads per row (k_gemv_n8), one CTA per tile, deep ring
+template <int WT, int EPI>
+static int launch_gemv8_t(b200_slice * s, GemvArgs a) {
+    constexpr int CB = chunk_bytes(WT);
+    auto kern = k_gemv_n8<WT, EPI>;
+    static bool attr_set[16] = {false};
+    const size_t stage = (size_t) kQS * 4 * CB;
+    const size_t act = (size_t) a.W.nbq * 144 + 34 * 8 + 64;
+    // every tile gets a co-resident CTA (13B: 160 tiles -> two CTAs on some SMs, each with half the ring)
+    const int need = (a.W.n_tiles + s->n_sm - 1) / s->n_sm;
+    const size_t budget = (size_t) kSmemLimit / need - 1024;
+    int NS = s->opt_ns > 0 ? s->opt_ns : (budget > act ? (int)((budget - act) / stage) : 2);
+    if (NS > 16) NS = 16;
+    if (NS < 2) NS = 2;
+    const size_t smem = NS * stage + act;
+    if (smem > (size_t) kSmemLimit) return fail(B200_EINVAL, "gemv8 needs %zu B of shared memory (K=%d)", smem, a.W.K);
+    if (!attr_set[s->device & 15]) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_set[s->device & 15] = true;
+    }
+    a.NS = NS; a.dbg_nomath = s->opt_nomath; a.pre_stages = s->opt_pre;
+    a.trace = nullptr;
+    if (s->trace && s->trace_next < 512) { a.trace = s->trace + (size_t) s->trace_next * 1024 * 8; s->trace_next++; s->trace_cls.push_back(s->cur_class); }
+    const int gx = a.W.n_tiles;
+    if (a.trace) s->trace_ctas.push_back(gx);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(gx, 1, 1);
+    cfg.blockDim = dim3(kN8Consumers + 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = s->use_pdl ? 1 : 0;
+    prof_begin(s);
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    prof_end(s);
+    s->launches++;
+    return 0;
+}
+// applies to: one column, ring on, Q4_0 / Q8_0, the matrix is narrow enough that k_gemv would run <= 1 CTA per SM
+static bool gemv8_applicable(const b200_slice * s, const PackedW & W, int N) {
+    return s->use_n8 && N == 1 && !s->cols && s->use_ring && (W.wtype == kWT_Q4_0 || W.wtype == kWT_Q8_0) && W.TR == 4 &&
+           W.n_tiles <= s->n_sm * 3 / 2;
+}
+template <int EPI>
+static int launch_gemv8(b200_slice * s, const GemvArgs & a) {
+    if (a.W.wtype == kWT_Q4_0) return launch_gemv8_t<kWT_Q4_0, EPI>(s, a);
+    return launch_gemv8_t<kWT_Q8_0, EPI>(s, a);
 }
 
 template <int WT, int G, int PRO, int EPI>
@@ -583,6 +635,7 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             o.nq_norm_w = Lw.ffn_norm; o.nq_counter = s->nq_counter; o.nq_partial = s->nq_partial; o.aq_out = s->aq_x; o.da_out = s->da_x; o.out_nbq = s->nbqE; o.out_dscale = dsc;
             if (D == 128) {
                 if (nq) { if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID_NQ>(s, o))) return rc; }
+                else if (gemv8_applicable(s, Lw.wo, N)) { if ((rc = launch_gemv8<EPI_RESID>(s, o))) return rc; }
                 else    { if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, o))) return rc; }
             } else {
                 if (nq) { if ((rc = launch_gemv<1, PRO_PLAIN, EPI_RESID_NQ>(s, o))) return rc; }
@@ -608,11 +661,13 @@ static int enqueue_layers(b200_slice * s, const float * in, int N, float * out) 
             } else if (s->fold_send && il == s->L - 1) {
                 w.mb_mine = (MailboxHdr *) s->mb_block;
                 w.mb_peer_inbox = (uint2 *)(s->mb_next + sizeof(MailboxHdr)); w.mb_slot_elems = s->mb_slot_floats;
-                if (s->wtype == kWT_Q4_0)      rc = launch_gemv_t<kWT_Q4_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
+                if (gemv8_applicable(s, Lw.w2, N)) rc = launch_gemv8<EPI_RESID_SEND>(s, w);
+                else if (s->wtype == kWT_Q4_0) rc = launch_gemv_t<kWT_Q4_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
                 else if (s->wtype == kWT_Q4_1) rc = launch_gemv_t<kWT_Q4_1, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
                 else                           rc = launch_gemv_t<kWT_Q8_0, 1, 1, PRO_PREQ, EPI_RESID_SEND, true>(s, w);
                 if (rc) return rc;
-            } else if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, w))) return rc;
+            } else if (gemv8_applicable(s, Lw.w2, N)) { if ((rc = launch_gemv8<EPI_RESID>(s, w))) return rc; }
+            else if ((rc = launch_gemv<1, PRO_PREQ, EPI_RESID>(s, w))) return rc;
         }
         cur = nxt;
     }
@@ -1130,7 +1185,8 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->use_nq    = env_int("B200_NQ", 0) != 0;   // grid-barrier norm+quant epilogue in wo / w2 (decode): exact, opt-in (its barrier costs what it saves)
     s->opt_ns = env_int("B200_NS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
     s->opt_pre = env_int("B200_PRE", 3); s->opt_nomath = env_int("B200_DBG_NOMATH", 0);
-    s->use_tiled_attn = env_int("B200_TILED_ATTN", 1) != 0;  // prompt chunks: query-tiled attention (K / V staged once per 16 queries)
+    s->use_tiled_attn = env_int("B200_TILED_ATTN", 1) != 0;
+    s->use_n8 = env_int("B200_N8", 0) != 0;          // single-token wo / w2: 8 threads per row (k_gemv_n8): exact, opt-in (slower: 806 vs 823 tok/s)  // prompt chunks: query-tiled attention (K / V staged once per 16 queries)
     s->f16_ring = env_int("B200_F16_RING", 1) != 0;          // F16-weight slices: TMA-ring matmul for single-token steps
     s->use_persist = env_int("B200_PERSIST", 0) != 0;         // single-token step as ONE persistent kernel (persist.cuh)
     s->persist_tr = env_int("B200_PERSIST_TR", 4); s->persist_ns = env_int("B200_PERSIST_NS", 0); s->persist_ctas = env_int("B200_PERSIST_CTAS", 0);

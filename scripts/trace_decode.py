@@ -40,6 +40,14 @@ for i in range(first, min(n, first + 5)):
             m = lambda a_, b_: np.median((d[:, a_] - d[:, b_]) / 1e3)
             print("        median phases: wait->rope/q %.2f | scores %.2f | cluster sync %.2f | softmax %.2f | V.p %.2f (incl. sync) | finish %.2f"
                   % (m(2, 1), m(4, 2), m(5, 4), m(6, 5), m(7, 6), m(3, 7)))
+        if names[cls[i]] != "attn" and (d[:, 7] > 0).any():
+            u = buf[i, :k, 7]
+            wait, tot = (u >> np.uint64(32)).astype(np.float64), (u & np.uint64(0xFFFFFFFF)).astype(np.float64)
+            fr = wait / np.maximum(tot, 1.0)
+            print("        main loop of warp 0: %.0f cycles median, of which waiting for weight stages %.0f%% / %.0f%% / %.0f%% (min / median / max)"
+                  % (np.median(tot), 100 * fr.min(), 100 * np.median(fr), 100 * fr.max()))
+        if names[cls[i]] == "attn":
+            pass
         elif (d[:, 5] > 0).any():
             print("        prologue split: load+sum %s | reduce+scale %s | quant+bar %s" % (q((d[:, 5] - d[:, 1]) / 1e3), q((d[:, 6] - d[:, 5]) / 1e3), q((d[:, 2] - d[:, 6]) / 1e3)))
     else:

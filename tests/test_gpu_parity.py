@@ -77,6 +77,17 @@ def test_launch_modes_agree(tmp_models, monkeypatch, pdl, graph, nq):
     assert bad == 0
 
 
+@pytest.mark.parametrize("n8", ["1", "0"])
+@pytest.mark.parametrize("shape,wtype", [("tiny128", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q8_0), ("tiny", ggjt.T_Q8_0)])
+def test_narrow_matrix_kernel_is_a_scheduling_choice(tmp_models, monkeypatch, n8, shape, wtype):
+    """Single-token wo / w2 run 8 threads per row (k_gemv_n8, one AVX lane per thread) instead of 4: the same lane chains."""
+    monkeypatch.setenv("B200_N8", n8)
+    sh = ggjt.SHAPES[shape]
+    path = tmp_models(shape, wtype, 0, 2)
+    bad, tot = _run_pair(path, [5, 1, 1, 1, 1, 30, 1, 1], sh)
+    assert bad == 0, "%d of %d floats differ" % (bad, tot)
+
+
 @pytest.mark.parametrize("ring,nq", [("1", "0"), ("0", "0"), ("0", "1")])
 def test_q4_1_launch_modes_agree(tmp_models, monkeypatch, ring, nq):
     """Q4_1 slices (unsigned nibbles + the scalar min chain, Q8_1 activations): the fused RMSNorm prologue (B200_NQ=0), the
