@@ -38,6 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             objs.append(o)
             cmd = [NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off",
                    "-I/usr/include", "-c", s, "-o", o]
+            cmd[1:1] = os.environ.get("B200_NVCC_DEFS", "").split()     # e.g. -DB200_TRACE_WAITS (profiles/r02_timeline_decode_waits.txt)
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

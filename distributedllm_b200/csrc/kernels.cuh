@@ -487,7 +487,9 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
 
     const int r = lane >> 2, w = lane & 3;
     int slot = 0, phase = 0;
+#ifdef B200_TRACE_WAITS                                                // special build (costs ~5 % of the step even when idle)
     long long dbg_wait = 0, dbg_t0 = a.trace ? clock64() : 0;      // B200_TRACE: cycles warp 0 waits for weight stages
+#endif
     uint2 * send_slot = nullptr; int send_seq = 0;
     if (EPI == EPI_RESID_SEND) {
         // last matmul of a pipelined slice (N = 1): every output row also goes, as {value, seq}, into the next rank's inbox
@@ -509,8 +511,11 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
         for (int s = 0; s < n_stage; s++) {
             const uint8_t * base;
             if (RING) {
+#ifdef B200_TRACE_WAITS
                 if (a.trace) { const long long c0 = clock64(); mbar_wait(&full[slot], phase); dbg_wait += clock64() - c0; }
-                else mbar_wait(&full[slot], phase);
+                else
+#endif
+                mbar_wait(&full[slot], phase);
                 base = ring + (size_t) slot * stage_bytes;
             } else {
                 base = gsrc + (size_t) s * stage_bytes;
@@ -671,8 +676,10 @@ __global__ void __launch_bounds__(kConsumers + 32) k_gemv(const GemvArgs a) {
         }
     }
     if (tid == 0) B200_TRACE(a.trace, 3);
+#ifdef B200_TRACE_WAITS
     if (tid == 0 && a.trace)                           // slot 7: (cycles spent waiting for weight stages) << 32 | main-loop cycles
         a.trace[((size_t) blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = ((unsigned long long) dbg_wait << 32) | (unsigned long long)((clock64() - dbg_t0) & 0xFFFFFFFFll);
+#endif
 }
 
 // =============================================================================================
@@ -770,12 +777,17 @@ __global__ void __launch_bounds__(kN8Consumers + 32) k_gemv_n8(const GemvArgs a)
         send_slot = a.mb_peer_inbox + (size_t)(send_seq & (kMbSlots - 1)) * a.mb_slot_elems;
     }
     int slot = 0, phase = 0;
+#ifdef B200_TRACE_WAITS
     long long dbg_wait = 0, dbg_t0 = a.trace ? clock64() : 0;
+#endif
     for (int tile = blockIdx.x; tile < a.W.n_tiles; tile += gridDim.x) {
         float acc = 0.f;
         for (int s = 0; s < n_stage; s++) {
+#ifdef B200_TRACE_WAITS
             if (a.trace) { const long long c0 = clock64(); mbar_wait(&full[slot], phase); dbg_wait += clock64() - c0; }
-            else mbar_wait(&full[slot], phase);
+            else
+#endif
+            mbar_wait(&full[slot], phase);
             const uint8_t * base = ring + (size_t) slot * stage_bytes + (size_t) rg * CB;
             if (!a.dbg_nomath)
             #pragma unroll
@@ -814,8 +826,10 @@ __global__ void __launch_bounds__(kN8Consumers + 32) k_gemv_n8(const GemvArgs a)
         }
     }
     if (tid == 0) B200_TRACE(a.trace, 3);
+#ifdef B200_TRACE_WAITS
     if (tid == 0 && a.trace)
         a.trace[(size_t) blockIdx.x * 8 + 7] = ((unsigned long long) dbg_wait << 32) | (unsigned long long)((clock64() - dbg_t0) & 0xFFFFFFFFll);
+#endif
 }
 
 // =============================================================================================
@@ -956,6 +970,132 @@ __global__ void __launch_bounds__(256) k_gemv_f16(const GemvF16Args a) {
             if (EPI == EPI_RESID) v = fadd(v, a.resid[(size_t) col * a.ldr + row]);
             if (EPI == EPI_GATE)  v = fmul(h2f(a.tsilu[f2h(res[0])]), res[1]);
             a.y[(size_t) col * a.ldy + row] = v;
+        }
+    }
+}
+
+// K1f-mc: the same F16 matmul for MULTI-token calls (prompt chunks, batched steps).  k_gemv_f16 takes one column per CTA, so
+// every token re-reads the whole matrix from L2 (405 MB per 7B layer and token: a 1024-token prompt ran at the L2 rate, 66 us per
+// token and layer, barely faster than decoding).  Here a CTA carries NC columns: the activations sit in shared memory as f32
+// (the fp16-rounded value widened, what h2f() would produce per use) interleaved [k][NC], so one 16-byte weight load and one
+// conversion per weight feed NC fma chains (LDS.128 = 4 columns).  Per column the chain is k_gemv_f16's, chunk for chunk.
+template <int PRO, int EPI, int NC>
+__global__ void __launch_bounds__(256) k_gemv_f16_mc(const GemvF16Args a) {
+    static_assert(NC == 4 || NC == 8, "columns per CTA");
+    extern __shared__ __align__(16) uint8_t smem[];
+    float * xf = (float *) smem;                     // [K][NC]
+    __shared__ double red[8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, K = a.K;
+    const int col0 = blockIdx.y * NC, ncols = min(NC, a.N - col0);
+    grid_dep_wait();
+    for (int n = 0; n < NC; n++) {
+        if (n >= ncols) { for (int i = tid; i < K; i += 256) xf[(size_t) i * NC + n] = 0.f; continue; }
+        const float * x = a.x + (size_t)(col0 + n) * a.ldx;
+        float scale = 1.0f;
+        if (PRO == PRO_NORM) {
+            double s = 0.0;
+            for (int i = tid; i < K; i += 256) s += (double) fmul(x[i], x[i]);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            __syncthreads();                         // red[] of the previous column has been read
+            if (lane == 0) red[warp] = s;
+            __syncthreads();
+            double tot = 0.0;
+            for (int i = 0; i < 8; i++) tot += red[i];
+            scale = __fdiv_rn(1.0f, __fsqrt_rn(fadd((float)(tot / (double) K), 1e-6f)));
+        }
+        for (int i = tid; i < K; i += 256) {
+            float v = x[i];
+            if (PRO == PRO_NORM) v = fmul(fmul(v, scale), a.norm_w[i]);
+            xf[(size_t) i * NC + n] = h2f(f2h(v));
+        }
+    }
+    __syncthreads();
+    const int nchunk = K / 32, nc8 = (nchunk + 7) / 8, ntail = K & 31;
+    // a warp owns TWO rows: every activation value read from shared memory feeds both (the LDS.128 stream, 4 bytes per
+    // weight and column, is what bounds this kernel once the weights are shared by NC columns)
+    for (int row0 = (blockIdx.x * 8 + warp) * 2; row0 < a.rows; row0 += gridDim.x * 16) {
+        const bool two = row0 + 1 < a.rows;
+        float res[2][2][NC];                                   // [matrix][row][column]
+        #pragma unroll
+        for (int m = 0; m < (EPI == EPI_GATE ? 2 : 1); m++) {
+            const uint16_t * Wm = m ? a.W2 : a.W;
+            const uint16_t * tl = m ? a.tail2 : a.tail;
+            float acc[2][NC];
+            #pragma unroll
+            for (int n = 0; n < NC; n++) { acc[0][n] = 0.f; acc[1][n] = 0.f; }
+            const uint4 * wp0 = (const uint4 *)(Wm + ((size_t) row0 * nc8 * 32 + lane) * 8);
+            const uint4 * wp1 = (const uint4 *)(Wm + ((size_t)(two ? row0 + 1 : row0) * nc8 * 32 + lane) * 8);
+            constexpr int U = 2;
+            uint4 v0[U], v1[U];
+            #pragma unroll
+            for (int q = 0; q < U; q++) {
+                v0[q] = q < nc8 ? __ldg(wp0 + (size_t) q * 32) : make_uint4(0, 0, 0, 0);
+                v1[q] = q < nc8 ? __ldg(wp1 + (size_t) q * 32) : make_uint4(0, 0, 0, 0);
+            }
+            for (int c8 = 0; c8 < nc8; c8 += U) {
+                uint4 n0[U], n1[U];                            // the next block's weights are on their way while this one is multiplied
+                #pragma unroll
+                for (int q = 0; q < U; q++) {
+                    n0[q] = c8 + U + q < nc8 ? __ldg(wp0 + (size_t)(c8 + U + q) * 32) : make_uint4(0, 0, 0, 0);
+                    n1[q] = c8 + U + q < nc8 ? __ldg(wp1 + (size_t)(c8 + U + q) * 32) : make_uint4(0, 0, 0, 0);
+                }
+                #pragma unroll
+                for (int q = 0; q < U; q++) {
+                    const uint32_t u0[4] = {v0[q].x, v0[q].y, v0[q].z, v0[q].w};
+                    const uint32_t u1[4] = {v1[q].x, v1[q].y, v1[q].z, v1[q].w};
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int c = (c8 + q) * 8 + j;
+                        if (c < nchunk) {
+                            const float w0 = h2f((uint16_t)(u0[j >> 1] >> (16 * (j & 1))));
+                            const float w1 = h2f((uint16_t)(u1[j >> 1] >> (16 * (j & 1))));
+                            const float4 * xp = (const float4 *)(xf + (size_t)(c * 32 + lane) * NC);
+                            #pragma unroll
+                            for (int n4 = 0; n4 < NC / 4; n4++) {
+                                const float4 xv = xp[n4];
+                                acc[0][n4*4]   = ffma(w0, xv.x, acc[0][n4*4]);   acc[0][n4*4+1] = ffma(w0, xv.y, acc[0][n4*4+1]);
+                                acc[0][n4*4+2] = ffma(w0, xv.z, acc[0][n4*4+2]); acc[0][n4*4+3] = ffma(w0, xv.w, acc[0][n4*4+3]);
+                                acc[1][n4*4]   = ffma(w1, xv.x, acc[1][n4*4]);   acc[1][n4*4+1] = ffma(w1, xv.y, acc[1][n4*4+1]);
+                                acc[1][n4*4+2] = ffma(w1, xv.z, acc[1][n4*4+2]); acc[1][n4*4+3] = ffma(w1, xv.w, acc[1][n4*4+3]);
+                            }
+                        }
+                    }
+                }
+                #pragma unroll
+                for (int q = 0; q < U; q++) { v0[q] = n0[q]; v1[q] = n1[q]; }
+            }
+            #pragma unroll
+            for (int rr = 0; rr < 2; rr++)
+                #pragma unroll
+                for (int n = 0; n < NC; n++) {
+                    float t = acc[rr][n];
+                    t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 16));
+                    t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 8));
+                    t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 4));
+                    t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 1));
+                    t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 2));
+                    double sumf = (double) t;
+                    const int row = (rr && two) ? row0 + 1 : row0;
+                    for (int i = 0; i < ntail; i++)
+                        sumf += (double) fmul(h2f(tl[(size_t) row * ntail + i]), xf[(size_t)(nchunk * 32 + i) * NC + n]);
+                    res[m][rr][n] = (float) sumf;
+                }
+        }
+        if (lane == 0) {
+            #pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                if (rr && !two) break;
+                const int row = row0 + rr;
+                #pragma unroll
+                for (int n = 0; n < NC; n++) {
+                    if (n < ncols) {
+                        float v = res[0][rr][n];
+                        if (EPI == EPI_RESID) v = fadd(v, a.resid[(size_t)(col0 + n) * a.ldr + row]);
+                        if (EPI == EPI_GATE)  v = fmul(h2f(a.tsilu[f2h(res[0][rr][n])]), res[1][rr][n]);
+                        a.y[(size_t)(col0 + n) * a.ldy + row] = v;
+                    }
+                }
+            }
         }
     }
 }

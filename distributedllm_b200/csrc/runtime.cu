@@ -66,7 +66,7 @@ struct b200_slice {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
     int64_t launches = 0, weight_bytes = 0;
-    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true, f16_ring = true, use_tiled_attn = true, use_n8 = false;
+    bool use_ring = true, use_graph = true, use_pdl = false, use_nq = true, f16_ring = true, use_tiled_attn = true, use_n8 = false, f16_mc = true; int f16_mc_cols = 4;
     bool skip_attention = false;   // measurement aid: replay only the weight matmuls of a step (bench.py roofline)
     bool fast_prefill = false; int fast_min_tokens = 32; uint16_t * xh = nullptr;   // tcgen05 prefill (fast mode)
     int fast_version = 2;                                                               // 2: fastgemm2.cuh (TMA tensor map, N = 256), 1: fastgemm.cuh
@@ -309,6 +309,29 @@ static int launch_f16(b200_slice * s, GemvF16Args a) {
         return 0;
     }
     int gx = (a.rows + 7) / 8;
+    if (a.N >= 2 && s->f16_mc) {
+        gx = (a.rows + 15) / 16;                         // 8 warps x 2 rows per CTA
+        // multi-token call: 8 (or 4) columns per CTA share every weight load (k_gemv_f16_mc)
+        // 4 columns per CTA keep the activation block at 64 KB for K = 4096: three CTAs (24 warps) per SM; B200_F16_MC=8 forces 8
+        const bool c8 = s->f16_mc_cols == 8 && a.N > 4 && (size_t) a.K * 4 * 8 + 64 <= (size_t) 200 * 1024;
+        const int nc = c8 ? 8 : 4;
+        const size_t msmem = (size_t) a.K * 4 * nc + 64;
+        if (msmem <= (size_t) 72 * 1024 || (c8 && msmem <= (size_t) kSmemLimit)) {
+            static bool mattr[16] = {false};
+            if (!mattr[s->device & 15]) {
+                B200_CUDA(cudaFuncSetAttribute(k_gemv_f16_mc<PRO, EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+                B200_CUDA(cudaFuncSetAttribute(k_gemv_f16_mc<PRO, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+                mattr[s->device & 15] = true;
+            }
+            const int ncolg = (a.N + nc - 1) / nc;
+            int per_sm = (int)(kSmemLimit / (msmem + 1024)); if (per_sm < 1) per_sm = 1;
+            int mgx = gx; const int mcap = (s->n_sm * per_sm + ncolg - 1) / ncolg;
+            if (mgx > mcap) mgx = mcap < 1 ? 1 : mcap;
+            if (c8) return launch_simple(s, k_gemv_f16_mc<PRO, EPI, 8>, dim3(mgx, ncolg, 1), dim3(256, 1, 1), msmem, a);
+            return launch_simple(s, k_gemv_f16_mc<PRO, EPI, 4>, dim3(mgx, ncolg, 1), dim3(256, 1, 1), msmem, a);
+        }
+    }
+    gx = (a.rows + 7) / 8;
     const int cap = s->n_sm * 8;
     if (gx > cap) gx = cap;
     return launch_simple(s, kern, dim3(gx, a.N, 1), dim3(256, 1, 1), smem, a);
@@ -1186,6 +1209,8 @@ int b200_slice_load_ex(const char * path, int device, int n_ctx, int n_sessions,
     s->opt_ns = env_int("B200_NS", 0); s->opt_cta_per_sm = env_int("B200_CTA_PER_SM", 0); s->opt_nc = env_int("B200_NC", 0);
     s->opt_pre = env_int("B200_PRE", 3); s->opt_nomath = env_int("B200_DBG_NOMATH", 0);
     s->use_tiled_attn = env_int("B200_TILED_ATTN", 1) != 0;
+    s->f16_mc = env_int("B200_F16_MC", 1) != 0;      // F16 slices, multi-token calls: 4 (8) columns per CTA share the weight loads
+    s->f16_mc_cols = env_int("B200_F16_MC", 1) == 8 ? 8 : 4;
     s->use_n8 = env_int("B200_N8", 0) != 0;          // single-token wo / w2: 8 threads per row (k_gemv_n8): exact, opt-in (slower: 806 vs 823 tok/s)  // prompt chunks: query-tiled attention (K / V staged once per 16 queries)
     s->f16_ring = env_int("B200_F16_RING", 1) != 0;          // F16-weight slices: TMA-ring matmul for single-token steps
     s->use_persist = env_int("B200_PERSIST", 0) != 0;         // single-token step as ONE persistent kernel (persist.cuh)

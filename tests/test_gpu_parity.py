@@ -77,6 +77,17 @@ def test_launch_modes_agree(tmp_models, monkeypatch, pdl, graph, nq):
     assert bad == 0
 
 
+@pytest.mark.parametrize("mc", ["1", "0"])
+@pytest.mark.parametrize("shape", ["tiny", "tiny3b", "tiny128"])
+def test_f16_multi_column_kernel_is_a_scheduling_choice(tmp_models, monkeypatch, mc, shape):
+    """F16 slices, multi-token calls: 8 / 4 columns per CTA share every weight load (k_gemv_f16_mc) or one column per CTA."""
+    monkeypatch.setenv("B200_F16_MC", mc)
+    sh = ggjt.SHAPES[shape]
+    path = tmp_models(shape, ggjt.T_F16, 0, 1)
+    bad, tot = _run_pair(path, [33, 2, 1, 5, 9, 1, 4], sh)
+    assert bad == 0, "%d of %d floats differ" % (bad, tot)
+
+
 @pytest.mark.parametrize("n8", ["1", "0"])
 @pytest.mark.parametrize("shape,wtype", [("tiny128", ggjt.T_Q4_0), ("tiny3b", ggjt.T_Q8_0), ("tiny", ggjt.T_Q8_0)])
 def test_narrow_matrix_kernel_is_a_scheduling_choice(tmp_models, monkeypatch, n8, shape, wtype):
