@@ -101,8 +101,8 @@ int b200_session_forward_device(b200_slice_t * s, int session, const float * d_i
 int b200_batch_forward(b200_slice_t * s, const int * sessions, int n_seq, const float * in, float * out);      /* host buffers */
 int b200_batch_forward_device(b200_slice_t * s, const int * sessions, int n_seq, const float * d_in, float * d_out, int sync);
 
-/* Fast mode for prefill calls (n_tokens >= min_tokens): the Q4_0 weight matmuls run on the tcgen05 tensor cores with
- * the dequantisation fused in (csrc/fastgemm.cuh).  NOT bit-exact: operands are rounded to fp16 after the reference's
+/* Fast mode for prefill calls (n_tokens >= min_tokens): the Q4_0 / Q8_0 weight matmuls run on the tcgen05 tensor cores with
+ * the dequantisation fused in (csrc/fastgemm2.cuh; Q4_1 and F16 slices ignore the switch and stay exact).  NOT bit-exact: operands are rounded to fp16 after the reference's
  * Q8_0 activation quantisation; deviation from exact mode is bounded in tests/test_gpu_fast_prefill.py.  Off by default
  * (or B200_FAST_PREFILL=1); decode steps always run in exact mode. */
 int b200_slice_set_fast_prefill(b200_slice_t * s, int on, int min_tokens);
