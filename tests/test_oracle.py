@@ -127,3 +127,25 @@ def test_q4_1_dot_is_scale_chain_plus_min_chain():
     blk = ggjt.quantize_q4_1(xw)
     step = (xw.reshape(4, 2, 32).max(2) - xw.reshape(4, 2, 32).min(2)) / 15
     assert (np.abs(ggjt.dequantize_q4_1(blk) - xw).reshape(4, 2, 32).max(2) <= step * 0.51 + 2e-3).all()
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_fast_q4_1_writer_files_are_valid_for_the_reference(tmp_path):
+    """The benchmark generator's Q4_1 files (random 20-byte blocks, ggjt.write_fast_q4_slice) load in the compiled reference
+    and the C restatement agrees with it on them, prompt and single-token steps."""
+    sh = ggjt.SHAPES["tiny128"]
+    path = str(tmp_path / "fast_q4_1.bin")
+    ggjt.write_fast_q4_slice(path, sh, 0, 1, 0, wtype=ggjt.T_Q4_1)
+    f = ggjt.read_file(path, sliced=True)
+    t = f.tensors["layers.0.feed_forward.w2.weight"]
+    assert t.ttype == ggjt.T_Q4_1 and t.nbytes == sh.n_embd * sh.n_ff // 32 * 20
+    w = ggjt.dequantize_q4_1(np.frombuffer(f.read_raw("layers.0.attention.wq.weight"), np.uint8).reshape(sh.n_embd, -1, 20))
+    assert abs(float(w.mean())) < 2e-3 and 0.7 < float(w.std()) * np.sqrt(sh.n_embd) < 1.3
+    ref, port = oracle.RefSlice(path, 3, 512), oracle.PortSlice(path, 512)
+    rng = np.random.default_rng(11)
+    for n in (20, 1, 1):
+        x = rng.standard_normal((n, sh.n_embd), dtype=np.float32)
+        a, b = ref.forward(x), port.forward(x)
+        assert np.isfinite(a).all() and (_bits(a) == _bits(b)).all()
+    ref.close()
+    port.close()
